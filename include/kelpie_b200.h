@@ -1,0 +1,180 @@
+/*
+ * kelpie_b200.h -- C ABI of the B200-native relevance-engine hot path.
+ *
+ * Drop-in boundary for rbarile17/kelpie (pure Python + torch; it has no FFI of its own,
+ * so each entry point names the Python call-sites it replaces; INTEGRATION.md shows the
+ * ctypes stub a maintainer adds on the reference side).
+ *
+ * Conventions
+ *   - every function returns 0 (KP_OK) or a negative KP_E* code; the message is kept per
+ *     context and read with kp_last_error(); nothing throws or exits across the ABI;
+ *   - all data-plane pointers are DEVICE pointers on the context's device unless the
+ *     parameter is documented as "host or device" (detected with cudaPointerGetAttributes);
+ *   - the caller (torch) owns every buffer it passes; the library owns only kp_ctx and
+ *     frees everything it allocated in kp_ctx_destroy();
+ *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*), the
+ *     calls are asynchronous unless stated otherwise;
+ *   - entity ids are int32 on the device (N < 2^31); ranks are int64 like the reference's;
+ *   - there is NO CPU fallback: without a CUDA device every call fails with KP_ECUDA.
+ */
+#ifndef KELPIE_B200_H
+#define KELPIE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KP_ABI_VERSION 1
+
+enum kp_status {
+  KP_OK = 0,
+  KP_EINVAL = -1,       /* bad argument */
+  KP_ECUDA = -2,        /* CUDA runtime / driver error (sticky errors reported as such) */
+  KP_ENOMEM = -3,       /* device allocation failed */
+  KP_EUNSUPPORTED = -4, /* valid request this build does not implement */
+  KP_ESTATE = -5        /* call order (e.g. rank with resident filter before kp_filter_upload) */
+};
+
+/* link_prediction/__init__.py:5-9 MODEL_REGISTRY */
+enum kp_model_kind { KP_TRANSE = 0, KP_COMPLEX = 1, KP_CONVE = 2 };
+
+/* Filtered-rank semantics.  "better" is < for the minimiser
+ * (TransE) and > for the maximisers (ComplEx, ConvE). */
+enum kp_rank_mode {
+  /* post_training_engine.py:110-114  filtered -> 1e6, target restored, #(score <= target) */
+  KP_RANK_ENGINE_MIN = 0,
+  /* post_training_engine.py:116-119  filtered -> -1e6 INCLUDING the target when it is in
+   * the filter, #(score >= target) counted before the target is restored */
+  KP_RANK_ENGINE_MAX = 1,
+  /* model.py:50-60  filtered -> +-1e6, target restored, #(<= target) or #(>= target) */
+  KP_RANK_MODEL = 2,
+  /* conve.py:160-184  filtered -> 0.0, target restored, 1 + position in a descending sort
+   * (ties resolved in index order) */
+  KP_RANK_CONVE_SORT = 3
+};
+
+enum kp_optimizer { KP_OPT_ADAGRAD = 0, KP_OPT_ADAM = 1, KP_OPT_SGD = 2 };
+
+typedef struct kp_ctx kp_ctx;
+
+/* Frozen ConvE network (conve.py:42-52; eval-mode batch-norm, conve.py:214-237).
+ * All pointers host or device, fp32, contiguous. */
+typedef struct kp_conve_weights {
+  const float* conv_w;   /* [n_filters,1,3,3] */
+  const float* conv_b;   /* [n_filters] */
+  const float* fc_w;     /* [dim, hidden] row-major (torch Linear.weight) */
+  const float* fc_b;     /* [dim] */
+  const float* bn1;      /* weight,bias,running_mean,running_var : 4 floats */
+  const float* bn2;      /* 4 x [n_filters] */
+  const float* bn3;      /* 4 x [dim] */
+  int32_t n_filters;     /* 32 */
+  int32_t hidden;        /* n_filters * (2*20-2) * (dim/20-2) */
+  float drop_input, drop_feature, drop_hidden; /* conve.py:34-36 */
+} kp_conve_weights;
+
+/* Hyper-parameters of one post-training (the `training` dict of configs/*.json as the
+ * reference's Kelpie*Optimizer consumes it). */
+typedef struct kp_hp {
+  int32_t epochs;
+  int32_t batch_size;
+  int32_t optimizer;      /* kp_optimizer; TransE/ConvE always Adam */
+  float lr;               /* ConvE: the caller passes 1e-3, see bce_optimizer.py:165 */
+  float beta1, beta2, eps;
+  float margin;           /* TransE pairwise_ranking_optimizer.py:44 */
+  float reg_weight;       /* TransE L2 / ComplEx N3 weight */
+  float label_smoothing;  /* ConvE bce_optimizer.py:108-110 */
+} kp_hp;
+
+/* One batch of C independent mimic post-trainings (one mimic row per candidate).
+ * Replaces Kelpie{PairwiseRanking,MultiClassNLL,BCE}Optimizer.train for C candidates
+ * (pairwise_ranking_optimizer.py:160-203, multiclass_nll_optimizer.py:138-164,
+ * bce_optimizer.py:161-208).  All index arrays are device int32 / int64; id N denotes
+ * the candidate's own mimic row.
+ *
+ * TransE / ComplEx: candidate c owns rows [row_off[c], row_off[c+1]) of `pos` (and `neg`),
+ * laid out epoch-major: epochs * rows_per_epoch[c] rows, in the order the reference
+ * visits them (after its shuffle / permutation); a step covers `batch_size` consecutive
+ * rows of one epoch.  TransE: neg[i] is the corrupted version of pos[i].
+ * If `static_epochs` != 0 the candidate stores ONE epoch of rows which is reused for
+ * every epoch (valid when an epoch is a single step: the loss is a mean over the batch,
+ * so the order inside the batch is irrelevant).
+ *
+ * ConvE: candidate c owns pairs [row_off[c], row_off[c+1]) of `pos` (columns: lhs, rel,
+ * unused) in er_vocab order (bce_optimizer.py:92-96); pair i's positives are
+ * pos_ids[pos_off[i] .. pos_off[i+1]).  There is no shuffling (bce_optimizer.py:167-176).
+ */
+typedef struct kp_pt_batch {
+  int32_t n_candidates;
+  int32_t static_epochs;
+  const int64_t* row_off;        /* [C+1] */
+  const int32_t* rows_per_epoch; /* [C] (ConvE: pairs per epoch) */
+  const int32_t* pos;            /* [rows,3] */
+  const int32_t* neg;            /* [rows,3] TransE only */
+  const int64_t* pos_off;        /* ConvE only, [pairs+1] */
+  const int32_t* pos_ids;        /* ConvE only */
+  const float* init_rows;        /* [C, D] */
+  float* out_rows;               /* [C, D] */
+  uint64_t dropout_seed;         /* ConvE with dropout > 0 */
+} kp_pt_batch;
+
+/* Queries of one scoring / ranking call: Q triples (s,p,o) int32 [Q,3] on the device.
+ * mimic_rows (nullable, [Q, D]): when given, entity id N means "row q of mimic_rows" and
+ * the score matrix has N+1 columns (KelpieModel.all_scores, model.py:107-108). */
+
+/* ---- context ------------------------------------------------------------------------- */
+
+/* Replaces the per-candidate clone()+cat of the tables (transe.py:86-99,
+ * complex.py:146-160, conve.py:206-212): tables are uploaded once (or borrowed when `ent`
+ * / `rel` already are device pointers) and the mimic row lives beside them.
+ * n_entities = N, n_relations2 = 2 * num_relations, dim = floats per row (2*d for
+ * ComplEx), norm = TransE p (1 or 2; ignored otherwise).  ent/rel: host or device. */
+int kp_ctx_create(int device, int model_kind, int64_t n_entities, int64_t n_relations2,
+                  int32_t dim, int32_t norm, const float* ent, const float* rel,
+                  const kp_conve_weights* conve, kp_ctx** out);
+int kp_ctx_destroy(kp_ctx* ctx);
+const char* kp_last_error(const kp_ctx* ctx); /* ctx may be NULL: last create error */
+int kp_abi_version(void);
+
+/* Device-resident CSR of the known facts, replacing the Python dict `Dataset.to_filter`
+ * (dataset.py:136-139): keys[i] = entity * n_relations2 + relation, strictly ascending;
+ * objs[offsets[i]..offsets[i+1]) = the DISTINCT ids to mask for that key, ascending.
+ * Direct keys (s,p) list objects, inverse keys (o,p+R) list subjects.  host or device. */
+int kp_filter_upload(kp_ctx* ctx, int64_t n_keys, const int64_t* keys, const int64_t* offsets,
+                     const int32_t* objs);
+
+/* ---- scoring / ranking --------------------------------------------------------------- */
+
+/* Model.all_scores (transe.py:48-65, complex.py:88-113, conve.py:133-158):
+ * out[q, j] = score of (s_q, p_q, j), row stride out_ld floats, N (+1) columns. */
+int kp_all_scores(kp_ctx* ctx, int32_t n_queries, const int32_t* triples,
+                  const float* mimic_rows, float* out, int64_t out_ld, void* stream);
+
+/* Filtered rank of the target o_q among all entities (post_training_engine.py:101-125,
+ * model.py:42-68, conve.py:160-184, engine.py:94-124), scores never materialised.
+ * Filter of query q: ids flt_ids[flt_off[q]..flt_off[q+1]) (ascending, distinct) when
+ * flt_off != NULL, else the resident CSR entry of key (s_q, p_q).
+ * Outputs (any may be NULL): target_score[Q], best_score[Q], rank[Q] (int64), and
+ * counters[Q,4] = {#strictly better, #ties, #ties with id < o, target-in-filter} over the
+ * unfiltered entities other than the target (what select_entities_to_convert needs). */
+int kp_filtered_rank(kp_ctx* ctx, int32_t n_queries, const int32_t* triples,
+                     const float* mimic_rows, const int64_t* flt_off, const int32_t* flt_ids,
+                     int32_t rank_mode, float* target_score, float* best_score, int64_t* rank,
+                     int32_t* counters, void* stream);
+
+/* ---- post-training --------------------------------------------------------------------- */
+
+int kp_post_train_batch(kp_ctx* ctx, const kp_pt_batch* batch, const kp_hp* hp, void* stream);
+
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+int64_t kp_launch_count(const kp_ctx* ctx);
+
+/* Set a tuning / debugging knob ("force_simt" = 1 routes GEMM-shaped passes through the
+ * CUDA-core kernels, used by the tests to cross-check the tcgen05 path). */
+int kp_set_option(kp_ctx* ctx, const char* name, int64_t value);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KELPIE_B200_H */

@@ -1,0 +1,209 @@
+// ConvE frozen network on the device: x = phi(lhs, rel) (conve.py:133-156, eval-mode BN):
+//   [lhs;rel] as a 40 x H image -> BN2d(1) -> Conv2d(1->F, 3x3) -> BN2d(F) -> ReLU -> flatten
+//   -> Linear(hidden -> D) -> BN1d(D) -> ReLU.
+// The entity projection x @ E^T + sigmoid is the generic all-entity pass (kp_pass.cu).
+#include "kp_internal.h"
+#include "kp_ptx.cuh"
+
+namespace {
+
+constexpr int CV_THREADS = 256;
+constexpr int CV_QB = 4;  // queries per CTA (share every fc_w row read)
+
+struct ConvK {
+  int Q, N, R2, D, H, F, hidden, stride;
+  const float* ent;
+  const float* rel;
+  const int32_t* triples;
+  const float* mimic;
+  const float *conv_w, *conv_b, *fc_w, *fc_b, *bn1, *bn2, *bn3;
+  float* x_out;      // [Q, D]
+  float* feat_out;   // nullable [Q, hidden]: post-ReLU feature maps (kept for the backward pass)
+};
+
+__device__ __forceinline__ void bn_affine(const float* bn, int n, int i, float& alpha, float& beta) {
+  // bn = {weight[n], bias[n], mean[n], var[n]}
+  const float inv = 1.f / sqrtf(bn[3 * n + i] + 1e-5f);
+  alpha = bn[i] * inv;
+  beta = bn[n + i] - bn[2 * n + i] * alpha;
+}
+
+__global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK p) {
+  extern __shared__ float sm[];
+  const int H = p.H, W2 = H - 2, D = p.D;
+  const int img_sz = 40 * H;
+  float* img = sm;                          // [QB][40*H]
+  float* feat = img + CV_QB * img_sz;       // [QB][hidden]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int qbase = blockIdx.x * CV_QB;
+
+  float a1, b1;
+  bn_affine(p.bn1, 1, 0, a1, b1);
+  for (int i = tid; i < CV_QB * img_sz; i += CV_THREADS) {
+    const int qb = i / img_sz, k = i % img_sz, q = qbase + qb;
+    float v = 0.f;
+    if (q < p.Q) {
+      const int s = p.triples[(size_t)q * p.stride], r = p.triples[(size_t)q * p.stride + 1];
+      if (k < D) {
+        const float* l = (s == p.N) ? p.mimic + (size_t)q * D : p.ent + (size_t)s * D;
+        v = l[k];
+      } else {
+        v = p.rel[(size_t)r * D + (k - D)];
+      }
+      v = v * a1 + b1;
+    }
+    img[i] = v;
+  }
+  __syncthreads();
+  const int per_f = 38 * W2;
+  for (int i = tid; i < CV_QB * p.hidden; i += CV_THREADS) {
+    const int qb = i / p.hidden, o = i % p.hidden;
+    const int c = o / per_f, y = (o % per_f) / W2, x = o % W2;
+    const float* im = img + qb * img_sz + y * H + x;
+    const float* w = p.conv_w + c * 9;
+    float acc = p.conv_b[c];
+#pragma unroll
+    for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+      for (int dx = 0; dx < 3; ++dx) acc = __fmaf_rn(w[dy * 3 + dx], im[dy * H + dx], acc);
+    float a2, b2;
+    bn_affine(p.bn2, p.F, c, a2, b2);
+    acc = fmaxf(acc * a2 + b2, 0.f);
+    feat[i] = acc;
+    if (p.feat_out && qbase + qb < p.Q) p.feat_out[(size_t)(qbase + qb) * p.hidden + o] = acc;
+  }
+  __syncthreads();
+  for (int k = warp; k < D; k += CV_THREADS / 32) {
+    const float* w = p.fc_w + (size_t)k * p.hidden;
+    float acc[CV_QB];
+#pragma unroll
+    for (int qb = 0; qb < CV_QB; ++qb) acc[qb] = 0.f;
+    for (int i = lane * 4; i < p.hidden; i += 128) {
+      const float4 wv = *reinterpret_cast<const float4*>(w + i);
+#pragma unroll
+      for (int qb = 0; qb < CV_QB; ++qb) {
+        const float4 f = *reinterpret_cast<const float4*>(feat + qb * p.hidden + i);
+        acc[qb] += wv.x * f.x + wv.y * f.y + wv.z * f.z + wv.w * f.w;
+      }
+    }
+#pragma unroll
+    for (int qb = 0; qb < CV_QB; ++qb) {
+      float v = acc[qb];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      acc[qb] = v;
+    }
+    if (lane == 0) {
+      float a3, b3;
+      bn_affine(p.bn3, D, k, a3, b3);
+#pragma unroll
+      for (int qb = 0; qb < CV_QB; ++qb)
+        if (qbase + qb < p.Q) p.x_out[(size_t)(qbase + qb) * D + k] = fmaxf((acc[qb] + p.fc_b[k]) * a3 + b3, 0.f);
+    }
+  }
+}
+
+__global__ void colsum_kernel(int N, int D, const float* __restrict__ ent, float* __restrict__ out) {
+  // one block per 32 columns; double accumulation keeps the sum exact enough for N ~ 1e6
+  const int k = blockIdx.x * 32 + (threadIdx.x & 31);
+  const int ry = threadIdx.x >> 5, ny = blockDim.x >> 5;
+  __shared__ double part[32][33];
+  double acc = 0.0;
+  if (k < D)
+    for (int j = ry; j < N; j += ny) acc += (double)ent[(size_t)j * D + k];
+  part[ry][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (ry == 0 && k < D) {
+    double s = 0.0;
+    for (int y = 0; y < ny; ++y) s += part[y][threadIdx.x & 31];
+    out[k] = (float)s;
+  }
+}
+
+template <typename T>
+int upload(kp_ctx* ctx, const T* src, size_t n, T** dst) {
+  void* d = nullptr;
+  cudaError_t e = cudaMalloc(&d, n * sizeof(T) + 16);
+  if (e != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "cudaMalloc(%zu): %s", n * sizeof(T), cudaGetErrorString(e));
+  ctx->owned.push_back(d);
+  KP_CUDA(ctx, cudaMemcpy(d, src, n * sizeof(T), cudaMemcpyDefault));
+  *dst = static_cast<T*>(d);
+  return KP_OK;
+}
+
+}  // namespace
+
+int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
+  const int D = ctx->D, H = D / 20;
+  if (w->n_filters <= 0 || w->hidden != w->n_filters * 38 * (H - 2))
+    KP_FAIL(ctx, KP_EINVAL, "ConvE hidden size %d != %d * 38 * %d", w->hidden, w->n_filters, H - 2);
+  if (w->hidden % 4 != 0) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size must be a multiple of 4");
+  if (!w->conv_w || !w->conv_b || !w->fc_w || !w->fc_b || !w->bn1 || !w->bn2 || !w->bn3)
+    KP_FAIL(ctx, KP_EINVAL, "null ConvE weight pointer");
+  ctx->cv.n_filters = w->n_filters;
+  ctx->cv.hidden = w->hidden;
+  ctx->cv.H = H;
+  ctx->cv.drop_in = w->drop_input;
+  ctx->cv.drop_fm = w->drop_feature;
+  ctx->cv.drop_hid = w->drop_hidden;
+  int rc;
+  if ((rc = upload(ctx, w->conv_w, (size_t)w->n_filters * 9, &ctx->cv.conv_w))) return rc;
+  if ((rc = upload(ctx, w->conv_b, (size_t)w->n_filters, &ctx->cv.conv_b))) return rc;
+  if ((rc = upload(ctx, w->fc_w, (size_t)D * w->hidden, &ctx->cv.fc_w))) return rc;
+  if ((rc = upload(ctx, w->fc_b, (size_t)D, &ctx->cv.fc_b))) return rc;
+  if ((rc = upload(ctx, w->bn1, 4, &ctx->cv.bn1))) return rc;
+  if ((rc = upload(ctx, w->bn2, (size_t)4 * w->n_filters, &ctx->cv.bn2))) return rc;
+  if ((rc = upload(ctx, w->bn3, (size_t)4 * D, &ctx->cv.bn3))) return rc;
+  void* cs = nullptr;
+  KP_CUDA(ctx, cudaMalloc(&cs, (size_t)D * 4));
+  ctx->owned.push_back(cs);
+  ctx->cv.ent_colsum = static_cast<float*>(cs);
+  colsum_kernel<<<(D + 31) / 32, 1024>>>((int)ctx->N, D, ctx->ent, ctx->cv.ent_colsum);
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}
+
+int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* triples, int stride, const float* mimic,
+                         float* x_out, float* feat_out, cudaStream_t st) {
+  ConvK p;
+  p.Q = Q;
+  p.N = (int)ctx->N;
+  p.R2 = (int)ctx->R2;
+  p.D = ctx->D;
+  p.H = ctx->cv.H;
+  p.F = ctx->cv.n_filters;
+  p.hidden = ctx->cv.hidden;
+  p.stride = stride;
+  p.ent = ctx->ent;
+  p.rel = ctx->rel;
+  p.triples = triples;
+  p.mimic = mimic;
+  p.conv_w = ctx->cv.conv_w;
+  p.conv_b = ctx->cv.conv_b;
+  p.fc_w = ctx->cv.fc_w;
+  p.fc_b = ctx->cv.fc_b;
+  p.bn1 = ctx->cv.bn1;
+  p.bn2 = ctx->cv.bn2;
+  p.bn3 = ctx->cv.bn3;
+  p.x_out = x_out;
+  p.feat_out = feat_out;
+  const size_t smem = (size_t)CV_QB * (40 * p.H + p.hidden) * sizeof(float);
+  static bool configured = false;
+  if (!configured) {
+    KP_CUDA(ctx, cudaFuncSetAttribute(conve_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  if (smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", p.hidden);
+  conve_features_kernel<<<(Q + CV_QB - 1) / CV_QB, CV_THREADS, smem, st>>>(p);
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}
+
+int kp_conve_features(kp_ctx* ctx, int Q, const int32_t* triples, int stride, const float* mimic, float* x_out,
+                      cudaStream_t st) {
+  return kp_conve_features_ex(ctx, Q, triples, stride, mimic, x_out, nullptr, st);
+}
+
+int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch*, const kp_hp*, cudaStream_t) {
+  KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE post-training is not built yet");
+}

@@ -1,0 +1,131 @@
+// Internal declarations shared by the translation units of libkelpie_b200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/kelpie_b200.h"
+
+struct kp_ctx {
+  int device = 0;
+  int kind = 0;
+  int64_t N = 0;   // entities (the mimic id is N)
+  int64_t R2 = 0;  // relations incl. inverses
+  int D = 0;       // floats per embedding row
+  int norm = 2;
+  int sm_count = 148;
+  const float* ent = nullptr;  // [N, D]
+  const float* rel = nullptr;  // [R2, D]
+  bool own_ent = false, own_rel = false;
+  CUtensorMap ent_map;  // TMA view of ent: box {32 floats, 128 rows}, 128B swizzle
+
+  // resident filter CSR (kp_filter_upload)
+  int64_t n_keys = 0;
+  int64_t* f_keys = nullptr;
+  int64_t* f_off = nullptr;
+  int32_t* f_ids = nullptr;
+
+  // ConvE frozen network (device copies) -- see kp_conve.cu
+  struct {
+    float *conv_w = nullptr, *conv_b = nullptr, *fc_w = nullptr, *fc_b = nullptr;
+    float *bn1 = nullptr, *bn2 = nullptr, *bn3 = nullptr;
+    float* ent_colsum = nullptr;  // [D] column sums of the entity table
+    int n_filters = 0, hidden = 0, H = 0;  // H = D / 20
+    float drop_in = 0, drop_fm = 0, drop_hid = 0;
+  } cv;
+
+  // grow-only device workspace arena
+  std::vector<void*> owned;
+  char* ws = nullptr;
+  size_t ws_bytes = 0;
+
+  int64_t launches = 0;
+  int64_t force_simt = 0;
+  std::string err;
+};
+
+#define KP_FAIL(ctx, code, ...)                          \
+  do {                                                   \
+    char _b[512];                                        \
+    snprintf(_b, sizeof(_b), __VA_ARGS__);               \
+    kp_set_error((ctx), _b);                             \
+    return (code);                                       \
+  } while (0)
+
+#define KP_CUDA(ctx, expr)                                                              \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess)                                                              \
+      KP_FAIL(ctx, KP_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),    \
+              __FILE__, __LINE__);                                                      \
+  } while (0)
+
+#define KP_LAUNCHED(ctx, n)                                                             \
+  do {                                                                                  \
+    (ctx)->launches += (n);                                                             \
+    cudaError_t _e = cudaGetLastError();                                                \
+    if (_e != cudaSuccess)                                                              \
+      KP_FAIL(ctx, KP_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
+              __FILE__, __LINE__);                                                      \
+  } while (0)
+
+void kp_set_error(kp_ctx* ctx, const char* msg);
+// workspace: returns a 1024B-aligned device pointer valid until the next kp_ws_reset
+int kp_ws_reserve(kp_ctx* ctx, size_t bytes);
+int kp_encode_2d_f32(kp_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols,
+                     int64_t ld_floats, int box_rows, int box_cols, bool swizzle128);
+
+struct WsCursor {
+  char* p;
+  char* end;
+  template <typename T>
+  T* take(size_t n) {
+    size_t b = (n * sizeof(T) + 1023) & ~size_t(1023);
+    T* r = reinterpret_cast<T*>(p);
+    p += b;
+    return r;
+  }
+  static size_t need(size_t n, size_t sz) { return (n * sz + 1023) & ~size_t(1023); }
+};
+
+// ---- kp_pass.cu : all-entity scoring pass (CUDA-core tile kernel) -------------------------
+enum { KP_OP_DOT = 0, KP_OP_L2 = 1, KP_OP_L1 = 2 };
+enum { KP_ACT_NONE = 0, KP_ACT_SIGMOID = 1 };
+
+struct kp_pass_args {
+  const float* qmat;  // [Qn padded to a multiple of 64, D] prepared query vectors
+  int Qn;
+  int op, act;
+  // STORE epilogue
+  float* out;
+  int64_t out_ld;
+  // RANK epilogue
+  bool rank;
+  bool minimize;
+  const float* target;     // [Qn]
+  const int32_t* tgt_ent;  // [Qn]
+  const int64_t* flt_beg;  // [Qn] ranges into flt_ids
+  const int64_t* flt_end;
+  const int32_t* flt_ids;
+  int32_t* cnt;     // [Qn,4] accumulated with atomics: strict, tie, tie_lo, -
+  uint32_t* best;   // [Qn] order-preserving uint encoding of the best other score
+};
+int kp_pass_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st);
+
+// ---- kp_score.cu : query preparation, rank finalisation ----------------------------------
+int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic, float* out,
+                  int64_t out_ld, const int64_t* flt_off, const int32_t* flt_ids, int mode,
+                  float* target_score, float* best_score, int64_t* rank, int32_t* counters,
+                  bool want_rank, cudaStream_t st);
+
+// ---- kp_transe_train.cu / kp_complex_train.cu / kp_conve.cu -------------------------------
+int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st);
+int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st);
+int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st);
+int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w);
+// features x = phi(lhs, rel) for Q (lhs,rel) pairs; lhs id N -> mimic row q
+int kp_conve_features(kp_ctx* ctx, int Q, const int32_t* triples, int stride, const float* mimic,
+                      float* x_out, cudaStream_t st);

@@ -1,0 +1,130 @@
+"""Host-side construction of post-training batches (the candidate batches the builders emit).
+
+A *job* is one mimic post-training: the mimic's training facts (ids, mimic id = N), its
+initial row and the hyper-parameters.  `draw_job` consumes the host random generators in
+EXACTLY the order the reference's Kelpie*Optimizer does and returns the
+index tables the CUDA kernels read, so that a batch of jobs drawn one after the other
+reproduces the reference's sequential run.
+"""
+from collections import defaultdict
+
+import numpy as np
+import torch
+
+
+def _rows_with_inverses(facts, num_relations):
+    """triples + inverse triples (dataset.py:319-331; *_optimizer.py train())."""
+    f = np.asarray(facts, dtype=np.int64).reshape(-1, 3)
+    inv = f.copy()
+    inv[:, 0], inv[:, 2] = f[:, 2], f[:, 0]
+    inv[:, 1] = f[:, 1] + num_relations
+    return np.vstack((f, inv)) if len(f) else np.zeros((0, 3), dtype=np.int64)
+
+
+def draw_transe(facts, num_relations, n_ent_with_mimic, hp):
+    """pairwise_ranking_optimizer.py:165-195.  Returns (rows_per_epoch, pos [E*n,3], neg [E*n,3])."""
+    rows = _rows_with_inverses(facts, num_relations)
+    n, E, ratio = len(rows), int(hp["epochs"]), int(hp["negative_triples_ratio"])
+    pos = np.empty((E, n, 3), dtype=np.int32)
+    neg = np.empty((E, n, 3), dtype=np.int32)
+    take = np.arange(n) // ratio  # first n rows of np.repeat(rows, ratio)
+    for e in range(E):
+        np.random.shuffle(rows)
+        rnd = torch.randint(high=n_ent_with_mimic, size=(ratio * n,))[:n].numpy()
+        coin = torch.randint(high=2, size=(ratio * n,))[:n].numpy()
+        p = rows[take]
+        pos[e] = p
+        neg[e] = p
+        head = coin == 1
+        neg[e, head, 0] = rnd[head]
+        neg[e, ~head, 2] = rnd[~head]
+    return n, pos.reshape(-1, 3), neg.reshape(-1, 3)
+
+
+def draw_complex(facts, num_relations, hp):
+    """multiclass_nll_optimizer.py:147-164.  Returns (rows_per_epoch, rows, static_epochs)."""
+    rows = _rows_with_inverses(facts, num_relations)
+    n, E = len(rows), int(hp["epochs"])
+    if n <= int(hp["batch_size"]):
+        # one step per epoch over ALL rows: the permutation cannot change a mean over the
+        # batch, so one epoch of rows is reused; the generator is still advanced as the
+        # reference's torch.randperm would.
+        for _ in range(E):
+            torch.randperm(n)
+        return n, rows.astype(np.int32), True
+    out = np.empty((E, n, 3), dtype=np.int32)
+    for e in range(E):
+        out[e] = rows[torch.randperm(n).numpy()]
+    return n, out.reshape(-1, 3), False
+
+
+def plan_conve(facts, num_relations):
+    """bce_optimizer.py:92-96: (lhs, rel) pairs in first-seen order and their positives."""
+    rows = _rows_with_inverses(facts, num_relations)
+    vocab = defaultdict(list)
+    for s, p, o in rows:
+        vocab[(int(s), int(p))].append(int(o))
+    pairs = np.array([(s, p, 0) for s, p in vocab], dtype=np.int32).reshape(-1, 3)
+    lens = [len(set(v)) for v in vocab.values()]
+    ids = np.array([x for v in vocab.values() for x in sorted(set(v))], dtype=np.int32)
+    return pairs, np.array(lens, dtype=np.int64), ids
+
+
+class Batch:
+    """Accumulates jobs and turns them into the flat arrays of kp_pt_batch."""
+
+    def __init__(self, kind, num_entities, num_relations, hp):
+        self.kind, self.N, self.R, self.hp = kind, int(num_entities), int(num_relations), hp
+        self.init_rows, self.rows_per_epoch = [], []
+        self.pos, self.neg, self.pos_lens, self.pos_ids = [], [], [], []
+        self.statics = []
+
+    def __len__(self):
+        return len(self.init_rows)
+
+    def add(self, facts, init_row):
+        """Draw (in reference order) and append one job; returns its index in the batch."""
+        if self.kind == "TransE":
+            n, pos, neg = draw_transe(facts, self.R, self.N + 1, self.hp)
+            self.pos.append(pos)
+            self.neg.append(neg)
+            static = False
+        elif self.kind == "ComplEx":
+            n, pos, static = draw_complex(facts, self.R, self.hp)
+            self.pos.append(pos)
+        else:
+            pos, lens, ids = plan_conve(facts, self.R)
+            n, static = len(pos), True
+            self.pos.append(pos)
+            self.pos_lens.append(lens)
+            self.pos_ids.append(ids)
+        self.statics.append(static)
+        self.rows_per_epoch.append(n)
+        self.init_rows.append(np.asarray(init_row, dtype=np.float32).reshape(-1))
+        return len(self.init_rows) - 1
+
+    def arrays(self):
+        static = all(self.statics)
+        if not static:  # mixed batch: unroll the single-epoch jobs so every job is epoch-major
+            E = int(self.hp["epochs"])
+            self.pos = [np.tile(p, (E, 1)) if st else p for p, st in zip(self.pos, self.statics)]
+            self.statics = [False] * len(self.statics)
+        sizes = [len(p) for p in self.pos]
+        row_off = np.zeros(len(sizes) + 1, dtype=np.int64)
+        row_off[1:] = np.cumsum(sizes)
+        out = dict(
+            init_rows=np.stack(self.init_rows).astype(np.float32),
+            row_off=row_off,
+            rows_per_epoch=np.array(self.rows_per_epoch, dtype=np.int32),
+            pos=np.concatenate(self.pos).astype(np.int32) if sum(sizes) else np.zeros((1, 3), np.int32),
+            static_epochs=static,
+        )
+        if self.kind == "TransE":
+            out["neg"] = np.concatenate(self.neg).astype(np.int32) if sum(sizes) else np.zeros((1, 3), np.int32)
+        if self.kind == "ConvE":
+            lens = np.concatenate(self.pos_lens) if self.pos_lens else np.zeros(0, np.int64)
+            off = np.zeros(len(lens) + 1, dtype=np.int64)
+            off[1:] = np.cumsum(lens)
+            out["pos_off"] = off
+            out["pos_ids"] = np.concatenate(self.pos_ids) if len(lens) else np.zeros(1, np.int32)
+        return out

@@ -1,0 +1,176 @@
+"""Necessary / sufficient post-training relevance engines
+(src/relevance_engines/post_training_engine.py:17-207).
+
+`compute_relevance(pred, triples)` keeps the reference's signature and result; the additive
+`compute_relevances(pred, [rules])` evaluates a whole batch of candidate explanations with one
+post-training launch sequence and one filtered-rank launch, drawing every random number in
+the order the sequential reference loop would (so the selected explanations are identical).
+"""
+import math
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from .. import plans, runtime
+from ..data import Dataset, KelpieDataset
+from ..link_prediction.models.model import KelpieModel, context_for
+from ..link_prediction.models.conve import burn_conve_constructor_rng
+from .engine import RelevanceEngine
+
+
+class PostTrainingEngine(RelevanceEngine):
+    @staticmethod
+    def sigmoid(x):
+        return 1 / (1 + math.exp(-x))
+
+    def __init__(self, model, dataset, hp: dict):
+        RelevanceEngine.__init__(self, model=model, dataset=dataset)
+        self.hp = hp
+        if isinstance(model, KelpieModel):
+            raise Exception("Already a post-trainable KelpieModel.")
+        # where KelpieTransE's xavier_normal_ draws (transe.py:93-95): the reference's mimic row
+        # lives on the GPU, so "cuda"; the CPU-patched oracle draws on the CPU generator.
+        self.rng_device = "cuda"
+        # replay the CPU-generator draws of KelpieConvE's discarded layer initialisers
+        self.replay_constructor_rng = True
+        self.set_cache()
+
+    def set_cache(self):
+        self.base_pt_results = {}
+        self.kelpie_dataset_cache_size = 20
+        self.kelpie_dataset_cache = OrderedDict()
+
+    def _get_kelpie_dataset(self, original_entity):
+        if original_entity not in self.kelpie_dataset_cache:
+            self.kelpie_dataset_cache[original_entity] = KelpieDataset(dataset=self.dataset, entity=original_entity)
+            self.kelpie_dataset_cache.move_to_end(original_entity)
+            if len(self.kelpie_dataset_cache) > self.kelpie_dataset_cache_size:
+                self.kelpie_dataset_cache.popitem(last=False)
+        return self.kelpie_dataset_cache[original_entity]
+
+    # ---- mimic row initialisation (transe.py:92-95, complex.py:155-157, conve.py:202-209) ----
+    def _init_row(self, init_tensor):
+        name = self.model.name
+        if name == "TransE":
+            row = init_tensor.clone().to(self.rng_device)
+            torch.nn.init.xavier_normal_(row)
+            return row.cpu().numpy()
+        if name == "ComplEx":
+            return (init_tensor.clone() * self.model.init_scale).numpy()
+        if self.replay_constructor_rng:
+            burn_conve_constructor_rng(self.model)
+        return init_tensor.clone().numpy()
+
+    def _apply(self, dataset, triples):
+        raise NotImplementedError
+
+    def _undo(self, dataset):
+        raise NotImplementedError
+
+    # ---- batched core ---------------------------------------------------------------------
+    def individual_results(self, items):
+        """[(pred, rule)] -> [(pt_results, base_pt_results)], RNG drawn in sequential-call order.
+
+        One mimic post-training job per candidate plus one per prediction whose homologous
+        (base) mimic is not cached yet (post_training_engine.py:46-62, 78-90)."""
+        model, kind = self.model, self.model.name
+        ctx = context_for(model)
+        N, R = self.dataset.num_entities, self.dataset.num_relations
+        batch = plans.Batch(kind, N, R, self.hp)
+        job_triple, job_filter = [], []
+        pending_base, slots = {}, []
+        for pred, rule in items:
+            pred = tuple(int(x) for x in pred)
+            ds = self._get_kelpie_dataset(pred[0])
+            kp = ds.as_kelpie_triple(pred)
+            init = torch.rand(1, model.dimension)  # post_training_engine.py:52 (CPU generator)
+            base_row = self._init_row(init)  # :55 -- built (and drawn) even when the base is cached
+            if pred not in self.base_pt_results and pred not in pending_base:
+                pending_base[pred] = batch.add(ds.kelpie_training_triples, base_row)
+                job_triple.append(kp)
+                job_filter.append(sorted(set(ds.to_filter.get((kp[0], kp[1]), []))))
+            pt_row = self._init_row(init)  # :59
+            self._apply(ds, rule)
+            j = batch.add(ds.kelpie_training_triples, pt_row)
+            job_triple.append(kp)
+            job_filter.append(sorted(set(ds.to_filter.get((kp[0], kp[1]), []))))
+            self._undo(ds)
+            slots.append((pred, j))
+
+        arrs = batch.arrays()
+        hp = runtime.make_hp(kind, self.hp)
+        rows = ctx.post_train(hp, **arrs)
+        flt_off = np.zeros(len(job_filter) + 1, dtype=np.int64)
+        flt_off[1:] = np.cumsum([len(f) for f in job_filter])
+        flt_ids = np.array([x for f in job_filter for x in f], dtype=np.int32)
+        mode = runtime.RANK_ENGINE_MIN if model.is_minimizer() else runtime.RANK_ENGINE_MAX
+        ts, bs, rk = ctx.filtered_rank(np.array(job_triple, dtype=np.int64), mode, mimic_rows=rows,
+                                       flt_off=flt_off, flt_ids=flt_ids if len(flt_ids) else None)
+        ts, bs, rk = ts.cpu().numpy(), bs.cpu().numpy(), rk.cpu().numpy()
+        self.last_rows = rows
+
+        def result(j):
+            return {"target_score": float(ts[j]), "best_score": torch.tensor(float(bs[j])),
+                    "target_rank": torch.tensor(int(rk[j]))}
+
+        for pred, j in pending_base.items():
+            self.base_pt_results[pred] = result(j)
+        return [(result(j), self.base_pt_results[pred]) for pred, j in slots]
+
+    def compute_relevance(self, pred, triples):
+        [(pt, base)] = self.individual_results([(pred, triples)])
+        return pt, base
+
+
+class NecessaryPostTrainingEngine(PostTrainingEngine):
+    def _apply(self, dataset, triples):
+        dataset.remove_training_triples(triples)
+
+    def _undo(self, dataset):
+        dataset.undo_removal()
+
+    def _relevance(self, pt, base):  # post_training_engine.py:136-145
+        rank_worsening = pt["target_rank"] - base["target_rank"]
+        score_worsening = (pt["target_score"] - base["target_score"] if self.model.is_minimizer()
+                           else base["target_score"] - pt["target_score"])
+        return float(rank_worsening + self.sigmoid(score_worsening))
+
+    def compute_relevance(self, pred, triples):
+        return self.compute_relevances(pred, [triples])[0]
+
+    def compute_relevances(self, pred, rules):
+        return [self._relevance(pt, base) for pt, base in self.individual_results([(pred, r) for r in rules])]
+
+
+class SufficientPostTrainingEngine(PostTrainingEngine):
+    def _apply(self, dataset, triples):
+        dataset.add_training_triples(triples)
+
+    def _undo(self, dataset):
+        dataset.undo_addition()
+
+    def _relevance(self, pt, base):  # post_training_engine.py:164-176
+        rank_improvement = base["target_rank"] - pt["target_rank"]
+        score_improvement = (base["target_score"] - pt["target_score"] if self.model.is_minimizer()
+                             else pt["target_score"] - base["target_score"])
+        relevance = float(rank_improvement + self.sigmoid(score_improvement))
+        return relevance / float(base["target_rank"])
+
+    def compute_individual_relevance(self, pred, triples):
+        [(pt, base)] = self.individual_results([(pred, triples)])
+        return self._relevance(pt, base)
+
+    def compute_relevance(self, pred, rule):
+        return self.compute_relevances(pred, [rule])[0]
+
+    def compute_relevances(self, pred, rules):
+        """post_training_engine.py:178-191 for every rule: rule-major, conversion-entity-minor."""
+        s = pred[0]
+        items = []
+        for rule in rules:
+            for e in self.entities_to_convert:
+                items.append((Dataset.replace_entity_in_triple(pred, s, e), Dataset.replace_entity_in_triples(rule, s, e)))
+        res = [self._relevance(pt, base) for pt, base in self.individual_results(items)]
+        k = len(self.entities_to_convert)
+        return [sum(res[i * k:(i + 1) * k]) / k for i in range(len(rules))]

@@ -1,0 +1,266 @@
+"""ctypes binding of libkelpie_b200.so (include/kelpie_b200.h) for PyTorch callers.
+
+PyTorch is plumbing here: it owns device memory and streams; every computation on the hot
+path happens inside the library's CUDA kernels.  There is no CPU fallback: if the library
+is missing or no sm_100 device is present, construction raises.
+"""
+import ctypes
+import os
+from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p
+
+import numpy as np
+import torch
+
+KP_TRANSE, KP_COMPLEX, KP_CONVE = 0, 1, 2
+KIND_ID = {"TransE": KP_TRANSE, "ComplEx": KP_COMPLEX, "ConvE": KP_CONVE}
+RANK_ENGINE_MIN, RANK_ENGINE_MAX, RANK_MODEL, RANK_CONVE_SORT = 0, 1, 2, 3
+OPT_ADAGRAD, OPT_ADAM, OPT_SGD = 0, 1, 2
+
+_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkelpie_b200.so")
+
+EXPORTS = [
+    "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
+    "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option",
+]
+
+
+class ConvEWeights(Structure):
+    _fields_ = [
+        ("conv_w", c_void_p), ("conv_b", c_void_p), ("fc_w", c_void_p), ("fc_b", c_void_p),
+        ("bn1", c_void_p), ("bn2", c_void_p), ("bn3", c_void_p),
+        ("n_filters", c_int32), ("hidden", c_int32),
+        ("drop_input", c_float), ("drop_feature", c_float), ("drop_hidden", c_float),
+    ]
+
+
+class HP(Structure):
+    _fields_ = [
+        ("epochs", c_int32), ("batch_size", c_int32), ("optimizer", c_int32),
+        ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
+        ("margin", c_float), ("reg_weight", c_float), ("label_smoothing", c_float),
+    ]
+
+
+class PTBatch(Structure):
+    _fields_ = [
+        ("n_candidates", c_int32), ("static_epochs", c_int32),
+        ("row_off", c_void_p), ("rows_per_epoch", c_void_p), ("pos", c_void_p), ("neg", c_void_p),
+        ("pos_off", c_void_p), ("pos_ids", c_void_p), ("init_rows", c_void_p), ("out_rows", c_void_p),
+        ("dropout_seed", c_uint64),
+    ]
+
+
+_lib = None
+
+
+def load_library():
+    """Load the in-tree shared library; raise (never fall back) when it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB_PATH):
+        raise RuntimeError(
+            f"{_LIB_PATH} is missing: build it with `python -m kelpie_b200.build` "
+            "(kelpie_b200 has no CPU or PyTorch fallback path)"
+        )
+    lib = ctypes.CDLL(_LIB_PATH)
+    lib.kp_ctx_create.argtypes = [c_int, c_int, c_int64, c_int64, c_int32, c_int32, c_void_p, c_void_p,
+                                  POINTER(ConvEWeights), POINTER(c_void_p)]
+    lib.kp_ctx_create.restype = c_int
+    lib.kp_ctx_destroy.argtypes = [c_void_p]
+    lib.kp_ctx_destroy.restype = c_int
+    lib.kp_last_error.argtypes = [c_void_p]
+    lib.kp_last_error.restype = c_char_p
+    lib.kp_abi_version.restype = c_int
+    lib.kp_filter_upload.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
+    lib.kp_filter_upload.restype = c_int
+    lib.kp_all_scores.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
+    lib.kp_all_scores.restype = c_int
+    lib.kp_filtered_rank.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
+                                     c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.kp_filtered_rank.restype = c_int
+    lib.kp_post_train_batch.argtypes = [c_void_p, POINTER(PTBatch), POINTER(HP), c_void_p]
+    lib.kp_post_train_batch.restype = c_int
+    lib.kp_launch_count.argtypes = [c_void_p]
+    lib.kp_launch_count.restype = c_int64
+    lib.kp_set_option.argtypes = [c_void_p, c_char_p, c_int64]
+    lib.kp_set_option.restype = c_int
+    _lib = lib
+    return lib
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _np_ptr(a):
+    return c_void_p(a.ctypes.data)
+
+
+def filter_csr(to_filter, n_relations2):
+    """Python dict {(entity, relation): [ids...]} -> (keys, offsets, ids) of kp_filter_upload.
+
+    The multiset lists of dataset.py:136-139 are de-duplicated and sorted: masking an id
+    twice is the same as masking it once.
+    """
+    items = [(int(e) * n_relations2 + int(r), sorted(set(int(x) for x in v))) for (e, r), v in to_filter.items() if len(v)]
+    items.sort(key=lambda kv: kv[0])
+    keys = np.array([k for k, _ in items], dtype=np.int64)
+    off = np.zeros(len(items) + 1, dtype=np.int64)
+    if items:
+        off[1:] = np.cumsum([len(v) for _, v in items])
+    ids = np.fromiter((x for _, v in items for x in v), dtype=np.int32, count=int(off[-1]))
+    return keys, off, ids
+
+
+class Context:
+    """One kp_ctx: device-resident tables + filter CSR of one model on one GPU."""
+
+    def __init__(self, kind, ent, rel, norm=2, conve=None, device=None):
+        self.lib = load_library()
+        if not torch.cuda.is_available():
+            raise RuntimeError("kelpie_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.device = torch.device("cuda", torch.cuda.current_device() if device is None else device)
+        self.kind = kind
+        # keep the tables alive: device tensors are borrowed by the library, not copied
+        self.ent = torch.as_tensor(ent, dtype=torch.float32).to(self.device).contiguous()
+        self.rel = torch.as_tensor(rel, dtype=torch.float32).to(self.device).contiguous()
+        self.N, self.D = self.ent.shape
+        self.R2 = self.rel.shape[0]
+        cw, self._conve_keep = None, None
+        if kind == "ConvE":
+            c = {k: torch.as_tensor(v, dtype=torch.float32).contiguous().cpu() for k, v in conve.items() if k != "dropout"}
+            bn = lambda i: torch.cat([c[f"bn{i}_w"].view(-1), c[f"bn{i}_b"].view(-1), c[f"bn{i}_mean"].view(-1), c[f"bn{i}_var"].view(-1)]).contiguous()
+            keep = dict(conv_w=c["conv_w"], conv_b=c["conv_b"], fc_w=c["fc_w"], fc_b=c["fc_b"], bn1=bn(1), bn2=bn(2), bn3=bn(3))
+            drop = conve.get("dropout", (0.0, 0.0, 0.0))
+            cw = ConvEWeights(*[c_void_p(keep[k].data_ptr()) for k in ("conv_w", "conv_b", "fc_w", "fc_b", "bn1", "bn2", "bn3")],
+                              int(c["conv_w"].shape[0]), int(c["fc_w"].shape[1]), float(drop[0]), float(drop[1]), float(drop[2]))
+            self._conve_keep = keep
+            self.dropout = tuple(float(x) for x in drop)
+        handle = c_void_p()
+        rc = self.lib.kp_ctx_create(self.device.index, KIND_ID[kind], self.N, self.R2, self.D, int(norm),
+                                    _ptr(self.ent), _ptr(self.rel), ctypes.byref(cw) if cw is not None else None,
+                                    ctypes.byref(handle))
+        if rc != 0:
+            raise RuntimeError(f"kp_ctx_create failed ({rc}): {self.lib.kp_last_error(None).decode()}")
+        self.handle = handle
+        self.has_filter = False
+
+    def close(self):
+        if getattr(self, "handle", None):
+            self.lib.kp_ctx_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed ({rc}): {self.lib.kp_last_error(self.handle).decode()}")
+
+    def _stream(self):
+        return c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def dev(self, a, dtype):
+        """numpy / tensor -> device tensor of `dtype` (pinned staging for host arrays)."""
+        if isinstance(a, torch.Tensor):
+            return a.to(device=self.device, dtype=dtype, non_blocking=True).contiguous()
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        if t.dtype != dtype:
+            t = t.to(dtype)
+        return t.pin_memory().to(self.device, non_blocking=True)
+
+    @property
+    def launches(self):
+        return int(self.lib.kp_launch_count(self.handle))
+
+    def set_option(self, name, value):
+        self._check(self.lib.kp_set_option(self.handle, name.encode(), int(value)), "kp_set_option")
+
+    def upload_filter(self, to_filter):
+        keys, off, ids = filter_csr(to_filter, self.R2)
+        self._check(self.lib.kp_filter_upload(self.handle, len(keys), _np_ptr(keys), _np_ptr(off), _np_ptr(ids)),
+                    "kp_filter_upload")
+        self.has_filter = True
+
+    def all_scores(self, triples, mimic_rows=None):
+        """[Q,3] int triples -> [Q, N(+1)] fp32 device tensor."""
+        t = self.dev(triples, torch.int32).view(-1, 3)
+        Q = t.shape[0]
+        m = None if mimic_rows is None else self.dev(mimic_rows, torch.float32).view(Q, self.D)
+        cols = self.N + (1 if m is not None else 0)
+        out = torch.empty((Q, cols), dtype=torch.float32, device=self.device)
+        self._check(self.lib.kp_all_scores(self.handle, Q, _ptr(t), _ptr(m), _ptr(out), cols, self._stream()),
+                    "kp_all_scores")
+        return out
+
+    def filtered_rank(self, triples, mode, mimic_rows=None, flt_off=None, flt_ids=None, counters=False):
+        """Returns (target_score[Q] f32, best_score[Q] f32, rank[Q] i64[, counters[Q,4] i32]) on device."""
+        t = self.dev(triples, torch.int32).view(-1, 3)
+        Q = t.shape[0]
+        m = None if mimic_rows is None else self.dev(mimic_rows, torch.float32).view(Q, self.D)
+        fo = None if flt_off is None else self.dev(flt_off, torch.int64)
+        fi = None if flt_ids is None else self.dev(flt_ids, torch.int32)
+        if fo is not None and fi is None:
+            fi = torch.zeros(1, dtype=torch.int32, device=self.device)
+        ts = torch.empty(Q, dtype=torch.float32, device=self.device)
+        bs = torch.empty(Q, dtype=torch.float32, device=self.device)
+        rk = torch.empty(Q, dtype=torch.int64, device=self.device)
+        cn = torch.empty((Q, 4), dtype=torch.int32, device=self.device) if counters else None
+        self._check(self.lib.kp_filtered_rank(self.handle, Q, _ptr(t), _ptr(m), _ptr(fo), _ptr(fi), int(mode),
+                                              _ptr(ts), _ptr(bs), _ptr(rk), _ptr(cn), self._stream()),
+                    "kp_filtered_rank")
+        return (ts, bs, rk, cn) if counters else (ts, bs, rk)
+
+    def post_train(self, hp, init_rows, row_off, rows_per_epoch, pos, neg=None, pos_off=None, pos_ids=None,
+                   static_epochs=False, dropout_seed=0):
+        """Run one batch of C mimic post-trainings; returns the [C, D] post-trained rows (device)."""
+        init = self.dev(init_rows, torch.float32).view(-1, self.D)
+        C = init.shape[0]
+        out = torch.empty_like(init)
+        keep = [init, out]
+
+        def d(a, dt):
+            if a is None:
+                return None
+            t = self.dev(a, dt)
+            keep.append(t)
+            return _ptr(t)
+
+        b = PTBatch(C, 1 if static_epochs else 0, d(row_off, torch.int64), d(rows_per_epoch, torch.int32),
+                    d(pos, torch.int32), d(neg, torch.int32), d(pos_off, torch.int64), d(pos_ids, torch.int32),
+                    _ptr(init), _ptr(out), int(dropout_seed))
+        self._check(self.lib.kp_post_train_batch(self.handle, ctypes.byref(b), ctypes.byref(hp), self._stream()),
+                    "kp_post_train_batch")
+        self._keep = keep  # inputs must outlive the asynchronous kernels
+        return out
+
+
+def make_hp(kind, hp):
+    """`training` dict of configs/*.json -> kp_hp, with the reference's effective values."""
+    h = HP()
+    h.epochs = int(hp["epochs"])
+    h.batch_size = int(hp["batch_size"])
+    h.beta1, h.beta2, h.eps = 0.9, 0.999, 1e-8
+    h.margin = h.reg_weight = h.label_smoothing = 0.0
+    if kind == "TransE":  # pairwise_ranking_optimizer.py:44-47
+        h.optimizer, h.lr = OPT_ADAM, float(hp["lr"])
+        h.margin, h.reg_weight = float(hp["margin"]), float(hp["regularizer_weight"])
+    elif kind == "ComplEx":  # multiclass_nll_optimizer.py:41-51
+        name = hp.get("optimizer_name", "Adagrad")
+        h.optimizer = {"Adagrad": OPT_ADAGRAD, "Adam": OPT_ADAM, "SGD": OPT_SGD}[name]
+        h.lr = float(hp["lr"])
+        if name == "Adam":
+            h.beta1, h.beta2 = float(hp["decay1"]), float(hp["decay2"])
+        if name == "Adagrad":
+            h.eps = 1e-10
+        h.reg_weight = float(hp["regularizer_weight"])
+        if hp.get("regularizer_name", "N3") != "N3" and h.reg_weight != 0:
+            raise NotImplementedError("only the N3 regulariser is implemented for ComplEx post-training")
+    else:  # bce_optimizer.py:165 -- Adam re-created with DEFAULT lr; the config lr is ignored
+        h.optimizer, h.lr = OPT_ADAM, 1e-3
+        h.label_smoothing = float(hp["label_smoothing"])
+    return h
