@@ -108,6 +108,9 @@ typedef struct kp_hp {
 typedef struct kp_pt_batch {
   int32_t n_candidates;
   int32_t static_epochs;
+  int32_t max_rows_per_epoch;    /* max over candidates of rows_per_epoch (host-known) */
+  int32_t reserved;
+  int64_t total_rows;            /* rows in `pos` = row_off[C] (host-known) */
   const int64_t* row_off;        /* [C+1] */
   const int32_t* rows_per_epoch; /* [C] (ConvE: pairs per epoch) */
   const int32_t* pos;            /* [rows,3] */

@@ -1,6 +1,300 @@
-// ComplEx mimic post-training (placeholder until the softmax pass lands).
+// Batched ComplEx mimic post-training (KelpieMultiClassNLLOptimizer,
+// multiclass_nll_optimizer.py:123-164; ComplEx.forward complex.py:59-86; N3 regularizers.py:37-46;
+// torch.optim.Adagrad / Adam / SGD).  SURVEY.md section 9.3 gives the arithmetic.
+//
+// Every row (h, r, t) of a mimic's training set mentions the mimic M.  Per optimiser step:
+//   * rows with h == M ("A rows"): the query q = e_M o R[r] changes every step.  One fused
+//     score->softmax->contract pass over the whole entity table gives, per row, the softmax
+//     statistics (m, l) and O = sum_j exp(z_j - m) E_j, i.e. d loss / d q without ever
+//     forming the [B, N+1] logits or the dense [N+1, 2d] table gradient of the reference.
+//   * rows with h != M ("B rows", t == M): their query and their log-sum-exp over the N
+//     frozen columns never change; both are computed ONCE per batch, after which a step costs
+//     one dot product with e_M (the gradient reaches e_M only through score column M).
+// The update kernel (one CTA per candidate) assembles d loss / d e_M from both row kinds and
+// column M, adds N3, and applies the optimiser step in place.
+#include "kp_flash.cuh"
 #include "kp_internal.h"
+#include "kp_plan.cuh"
 
-int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch*, const kp_hp*, cudaStream_t) {
-  KP_FAIL(ctx, KP_EUNSUPPORTED, "ComplEx post-training is not built yet");
+namespace {
+
+// q = lhs o rel (complex product), lhs = mimic row of cand[g] when lhs_id == NULL (A rows)
+__global__ void cx_build_queries(int G, int D, const float* __restrict__ ent, const float* __restrict__ rel,
+                                 const float* __restrict__ mim, const int32_t* __restrict__ cand,
+                                 const int32_t* __restrict__ lhs_id, const int32_t* __restrict__ rel_id,
+                                 float* __restrict__ qmat) {
+  const int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (g >= G) return;
+  const float* l = lhs_id ? ent + (size_t)lhs_id[g] * D : mim + (size_t)cand[g] * D;
+  const float* r = rel + (size_t)rel_id[g] * D;
+  float* out = qmat + (size_t)g * D;
+  const int d = D >> 1;
+  for (int k = lane; k < d; k += 32) {
+    const float lr = l[k], li = l[d + k], rr = r[k], ri = r[d + k];
+    out[k] = __fsub_rn(__fmul_rn(lr, rr), __fmul_rn(li, ri));
+    out[d + k] = __fadd_rn(__fmul_rn(lr, ri), __fmul_rn(li, rr));
+  }
+}
+
+// lse over the frozen columns of each B row, from the per-strip softmax statistics
+__global__ void cx_lse(int G, int n_strips, const float* __restrict__ pm, const float* __restrict__ pl,
+                       float* __restrict__ lse) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  float M, L;
+  kp_flash_merge_stats(pm, pl, n_strips, G, g, M, L);
+  lse[g] = M + logf(L);
+}
+
+struct CxUpd {
+  int C, N, D, GA, n_strips, optimizer;
+  long long step;  // 1-based optimiser step (Adam bias correction)
+  float lr, beta1, beta2, eps, n3;
+  const float* ent;
+  const float* rel;
+  const int32_t *nA, *nB, *nSelf;
+  const int64_t *aoff, *boff;
+  const int32_t *a_rel, *a_truth;
+  const float* qA;      // [GA, D]
+  const float* pm;      // [n_strips, GA]
+  const float* pl;
+  const float* pO;      // [n_strips, GA, D]
+  const float* qB;      // [GB, D]
+  const float* lseB;    // [GB]
+  float* mim;           // [C, D]
+  float* st1;           // [C, D] Adagrad sum / Adam exp_avg
+  float* st2;           // [C, D] Adam exp_avg_sq
+};
+
+constexpr int UPD_THREADS = 256;
+
+__device__ __forceinline__ float block_sum(float v, float* red) {
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < UPD_THREADS / 32; ++w) s += red[w];
+  return s;
+}
+
+__global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
+  extern __shared__ float usm[];
+  const int D = p.D, d = D >> 1;
+  float* eM = usm;         // [D]
+  float* grad = eM + D;    // [D]
+  float* dq = grad + D;    // [D]
+  float* qv = dq + D;      // [D]
+  __shared__ float red[UPD_THREADS / 32];
+  const int c = blockIdx.x, tid = threadIdx.x;
+  const int nA = p.nA[c], nB = p.nB[c];
+  const int B = nA + nB;
+  if (B == 0) return;  // candidate has no step here (finished, or no facts)
+  const float invB = 1.f / (float)B;
+  for (int k = tid; k < D; k += UPD_THREADS) {
+    eM[k] = p.mim[(size_t)c * D + k];
+    grad[k] = 0.f;
+  }
+  __syncthreads();
+
+  for (int64_t g = p.aoff[c]; g < p.aoff[c] + nA; ++g) {
+    float M, L;
+    kp_flash_merge_stats(p.pm, p.pl, p.n_strips, p.GA, (int)g, M, L);
+    float part = 0.f;
+    for (int k = tid; k < D; k += UPD_THREADS) {
+      const float qk = p.qA[(size_t)g * D + k];
+      qv[k] = qk;
+      part = __fmaf_rn(qk, eM[k], part);
+    }
+    const float zM = block_sum(part, red);
+    const float mx = fmaxf(M, zM);
+    const float eF = L * expf(M - mx), eS = expf(zM - mx);
+    const float den = eF + eS;
+    const float pM = eS / den;
+    const int o = p.a_truth[g];
+    const float* Eo = (o == p.N) ? eM : p.ent + (size_t)o * D;
+    for (int k = tid; k < D; k += UPD_THREADS) {
+      float ok = 0.f;
+      for (int s = 0; s < p.n_strips; ++s) {
+        const float ms = p.pm[(size_t)s * p.GA + g];
+        if (ms != -INFINITY) ok += p.pO[((size_t)s * p.GA + g) * D + k] * expf(ms - M);
+      }
+      dq[k] = (ok * (expf(M - mx) / den) + pM * eM[k] - Eo[k]) * invB;
+    }
+    __syncthreads();
+    const float* rho = p.rel + (size_t)p.a_rel[g] * D;
+    const float colM = (pM - (o == p.N ? 1.f : 0.f)) * invB;
+    for (int k = tid; k < d; k += UPD_THREADS) {
+      const float rr = rho[k], ri = rho[d + k], da = dq[k], db = dq[d + k];
+      grad[k] += da * rr + db * ri + colM * qv[k];
+      grad[d + k] += -da * ri + db * rr + colM * qv[d + k];
+    }
+    __syncthreads();
+  }
+  for (int64_t b = p.boff[c]; b < p.boff[c] + nB; ++b) {
+    float part = 0.f;
+    for (int k = tid; k < D; k += UPD_THREADS) {
+      const float qk = p.qB[(size_t)b * D + k];
+      qv[k] = qk;
+      part = __fmaf_rn(qk, eM[k], part);
+    }
+    const float z = block_sum(part, red);
+    const float lse = p.lseB[b];
+    const float mx = fmaxf(lse, z);
+    const float eS = expf(z - mx);
+    const float pM = eS / (expf(lse - mx) + eS);
+    const float coef = (pM - 1.f) * invB;  // the truth of a B row is the mimic itself
+    for (int k = tid; k < D; k += UPD_THREADS) grad[k] += coef * qv[k];
+    __syncthreads();
+  }
+  // N3 (regularizers.py:37-46): w/B * sum_rows |f|^3, f = sqrt(re^2 + im^2) of lhs and rhs rows
+  const float cntM = (float)(nA + nB + p.nSelf[c]);
+  double bc1 = 1.0, bc2 = 1.0;
+  if (p.optimizer == KP_OPT_ADAM) {
+    bc1 = 1.0 - pow((double)p.beta1, (double)p.step);
+    bc2 = 1.0 - pow((double)p.beta2, (double)p.step);
+  }
+  for (int k = tid; k < D; k += UPD_THREADS) {
+    float g = grad[k];
+    const float e = eM[k];
+    if (p.n3 != 0.f) {
+      const int kr = (k < d) ? k : k - d;
+      const float f = sqrtf(eM[kr] * eM[kr] + eM[kr + d] * eM[kr + d]);
+      g += 3.f * p.n3 * invB * cntM * f * e;
+    }
+    const size_t idx = (size_t)c * D + k;
+    float out;
+    if (p.optimizer == KP_OPT_ADAGRAD) {
+      const float s = p.st1[idx] + g * g;
+      p.st1[idx] = s;
+      out = e - p.lr * (g / (sqrtf(s) + p.eps));
+    } else if (p.optimizer == KP_OPT_ADAM) {
+      const float m = p.st1[idx] + (1.f - p.beta1) * (g - p.st1[idx]);
+      const float v = p.st2[idx] * p.beta2 + (1.f - p.beta2) * g * g;
+      p.st1[idx] = m;
+      p.st2[idx] = v;
+      const float denom = sqrtf(v) / (float)sqrt(bc2) + p.eps;
+      out = e - (float)((double)p.lr / bc1) * (m / denom);
+    } else {
+      out = e - p.lr * g;
+    }
+    p.mim[idx] = out;
+  }
+}
+
+}  // namespace
+
+int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st) {
+  if (!b->pos) KP_FAIL(ctx, KP_EINVAL, "ComplEx post-training needs rows");
+  const int C = b->n_candidates, D = ctx->D;
+  const int bs = hp->batch_size;
+  const int max_n = b->max_rows_per_epoch;
+  if (max_n < 0 || b->total_rows < 0) KP_FAIL(ctx, KP_EINVAL, "bad batch totals");
+  const int spe_max = max_n > 0 ? (max_n + bs - 1) / bs : 0;
+  const long long T = (long long)hp->epochs * spe_max;
+  const bool static_plan = b->static_epochs != 0 && spe_max <= 1;
+  // upper bound on rows taking part in one step
+  int64_t cap = (int64_t)C * (int64_t)(max_n < bs ? max_n : bs);
+  if (b->static_epochs == 0 && hp->epochs > 0) {
+    const int64_t per_epoch = b->total_rows / hp->epochs;
+    if (per_epoch < cap) cap = per_epoch;
+  } else if (b->total_rows < cap) {
+    cap = b->total_rows;
+  }
+  if (cap < 1) cap = 1;
+  if (cap > (int64_t)1 << 30) KP_FAIL(ctx, KP_EUNSUPPORTED, "batch too large (%lld rows per step)", (long long)cap);
+  const int G = (int)cap;
+  const int Gpad = ((G + 63) / 64) * 64;
+  int n_strips = 1;
+  kp_flash_plan(ctx, 16, &n_strips);  // worst case (few rows -> many strips)
+  const int S = n_strips > 64 ? 64 : n_strips;
+
+  size_t need = 0;
+  need += 3 * WsCursor::need((size_t)C * D, 4);         // mim, st1, st2
+  need += 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8);
+  need += 6 * WsCursor::need(G, 4);
+  need += 2 * WsCursor::need((size_t)Gpad * D, 4);      // qA, qB
+  need += WsCursor::need(G, 4);                          // lseB
+  need += 2 * WsCursor::need((size_t)S * G, 4) + WsCursor::need((size_t)S * G * D, 4);
+  int rc = kp_ws_reserve(ctx, need);
+  if (rc != KP_OK) return rc;
+  WsCursor ws{ctx->ws, ctx->ws + ctx->ws_bytes};
+  float* mim = ws.take<float>((size_t)C * D);
+  float* st1 = ws.take<float>((size_t)C * D);
+  float* st2 = ws.take<float>((size_t)C * D);
+  CxPlan pl;
+  pl.C = C; pl.N = (int)ctx->N; pl.D = D; pl.bs = bs; pl.epochs = hp->epochs; pl.static_epochs = b->static_epochs; pl.truth_is_row = 0;
+  pl.row_off = b->row_off; pl.rows_per_epoch = b->rows_per_epoch; pl.pos = b->pos;
+  pl.nA = ws.take<int32_t>(C); pl.nB = ws.take<int32_t>(C); pl.nSelf = ws.take<int32_t>(C);
+  pl.aoff = ws.take<int64_t>(C + 1); pl.boff = ws.take<int64_t>(C + 1);
+  pl.a_cand = ws.take<int32_t>(G); pl.a_rel = ws.take<int32_t>(G); pl.a_truth = ws.take<int32_t>(G);
+  pl.b_cand = ws.take<int32_t>(G); pl.b_lhs = ws.take<int32_t>(G); pl.b_rel = ws.take<int32_t>(G);
+  float* qA = ws.take<float>((size_t)Gpad * D);
+  float* qB = ws.take<float>((size_t)Gpad * D);
+  float* lseB = ws.take<float>(G);
+  float* pm = ws.take<float>((size_t)S * G);
+  float* plv = ws.take<float>((size_t)S * G);
+  float* pO = ws.take<float>((size_t)S * G * D);
+
+  KP_CUDA(ctx, cudaMemcpyAsync(mim, b->init_rows, (size_t)C * D * 4, cudaMemcpyDeviceToDevice, st));
+  KP_CUDA(ctx, cudaMemsetAsync(st1, 0, (size_t)C * D * 4, st));
+  KP_CUDA(ctx, cudaMemsetAsync(st2, 0, (size_t)C * D * 4, st));
+
+  const int cb = (C + 127) / 128;
+  int64_t GA = 0, GB = 0;
+  auto make_plan = [&](int t) -> int {
+    cx_count<<<cb, 128, 0, st>>>(pl, t);
+    cx_scan<<<1, 1024, 0, st>>>(pl);
+    cx_assign<<<cb, 128, 0, st>>>(pl, t);
+    KP_LAUNCHED(ctx, 3);
+    int64_t tot[2];
+    KP_CUDA(ctx, cudaMemcpyAsync(&tot[0], pl.aoff + C, 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(ctx, cudaMemcpyAsync(&tot[1], pl.boff + C, 8, cudaMemcpyDeviceToHost, st));
+    KP_CUDA(ctx, cudaStreamSynchronize(st));
+    GA = tot[0];
+    GB = tot[1];
+    if (GA > G || GB > G) KP_FAIL(ctx, KP_EINVAL, "step uses more rows (%lld/%lld) than the batch declares (%d)", (long long)GA, (long long)GB, G);
+    if (GB > 0) {
+      cx_build_queries<<<(int)((GB + 7) / 8), 256, 0, st>>>((int)GB, D, ctx->ent, ctx->rel, nullptr, nullptr, pl.b_lhs, pl.b_rel, qB);
+      KP_LAUNCHED(ctx, 1);
+      int ns = 1;
+      kp_flash_plan(ctx, (int)GB, &ns);
+      int r2 = kp_flash_simt(ctx, qB, (int)GB, KP_FLASH_SOFTMAX, pm, plv, pO, st);
+      if (r2 != KP_OK) return r2;
+      cx_lse<<<(int)((GB + 255) / 256), 256, 0, st>>>((int)GB, ns, pm, plv, lseB);
+      KP_LAUNCHED(ctx, 1);
+    }
+    return KP_OK;
+  };
+
+  for (long long t = 0; t < T; ++t) {
+    if (t == 0 || !static_plan) {
+      if ((rc = make_plan((int)t)) != KP_OK) return rc;
+    }
+    int ns = 1;
+    if (GA > 0) {
+      cx_build_queries<<<(int)((GA + 7) / 8), 256, 0, st>>>((int)GA, D, ctx->ent, ctx->rel, mim, pl.a_cand, nullptr, pl.a_rel, qA);
+      KP_LAUNCHED(ctx, 1);
+      kp_flash_plan(ctx, (int)GA, &ns);
+      if ((rc = kp_flash_simt(ctx, qA, (int)GA, KP_FLASH_SOFTMAX, pm, plv, pO, st)) != KP_OK) return rc;
+    }
+    if (GA + GB > 0) {
+      CxUpd u;
+      u.C = C; u.N = (int)ctx->N; u.D = D; u.GA = (int)GA; u.n_strips = ns; u.optimizer = hp->optimizer;
+      u.step = t + 1;
+      u.lr = hp->lr; u.beta1 = hp->beta1; u.beta2 = hp->beta2; u.eps = hp->eps; u.n3 = hp->reg_weight;
+      u.ent = ctx->ent; u.rel = ctx->rel;
+      u.nA = pl.nA; u.nB = pl.nB; u.nSelf = pl.nSelf; u.aoff = pl.aoff; u.boff = pl.boff;
+      u.a_rel = pl.a_rel; u.a_truth = pl.a_truth;
+      u.qA = qA; u.pm = pm; u.pl = plv; u.pO = pO; u.qB = qB; u.lseB = lseB;
+      u.mim = mim; u.st1 = st1; u.st2 = st2;
+      cx_update<<<C, UPD_THREADS, (size_t)4 * D * sizeof(float), st>>>(u);
+      KP_LAUNCHED(ctx, 1);
+    }
+  }
+  KP_CUDA(ctx, cudaMemcpyAsync(b->out_rows, mim, (size_t)C * D * 4, cudaMemcpyDeviceToDevice, st));
+  return KP_OK;
 }

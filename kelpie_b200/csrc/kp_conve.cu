@@ -14,8 +14,10 @@ struct ConvK {
   int Q, N, R2, D, H, F, hidden, stride;
   const float* ent;
   const float* rel;
-  const int32_t* triples;
-  const float* mimic;
+  const int32_t* lhs_ids;      // [Q*stride] entity id of the lhs (N = mimic); NULL = every lhs is a mimic
+  const int32_t* rel_ids;      // [Q*stride]
+  const float* mimic;          // mimic rows
+  const int32_t* mimic_index;  // row of `mimic` used by query q (NULL: row q)
   const float *conv_w, *conv_b, *fc_w, *fc_b, *bn1, *bn2, *bn3;
   float* x_out;      // [Q, D]
   float* feat_out;   // nullable [Q, hidden]: post-ReLU feature maps (kept for the backward pass)
@@ -43,9 +45,9 @@ __global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK 
     const int qb = i / img_sz, k = i % img_sz, q = qbase + qb;
     float v = 0.f;
     if (q < p.Q) {
-      const int s = p.triples[(size_t)q * p.stride], r = p.triples[(size_t)q * p.stride + 1];
+      const int s = p.lhs_ids ? p.lhs_ids[(size_t)q * p.stride] : p.N, r = p.rel_ids[(size_t)q * p.stride];
       if (k < D) {
-        const float* l = (s == p.N) ? p.mimic + (size_t)q * D : p.ent + (size_t)s * D;
+        const float* l = (s == p.N) ? p.mimic + (size_t)(p.mimic_index ? p.mimic_index[q] : q) * D : p.ent + (size_t)s * D;
         v = l[k];
       } else {
         v = p.rel[(size_t)r * D + (k - D)];
@@ -163,8 +165,9 @@ int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
   return KP_OK;
 }
 
-int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* triples, int stride, const float* mimic,
-                         float* x_out, float* feat_out, cudaStream_t st) {
+int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32_t* rel_ids, int stride,
+                         const float* mimic, const int32_t* mimic_index, float* x_out, float* feat_out,
+                         cudaStream_t st) {
   ConvK p;
   p.Q = Q;
   p.N = (int)ctx->N;
@@ -176,8 +179,10 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* triples, int stride,
   p.stride = stride;
   p.ent = ctx->ent;
   p.rel = ctx->rel;
-  p.triples = triples;
+  p.lhs_ids = lhs_ids;
+  p.rel_ids = rel_ids;
   p.mimic = mimic;
+  p.mimic_index = mimic_index;
   p.conv_w = ctx->cv.conv_w;
   p.conv_b = ctx->cv.conv_b;
   p.fc_w = ctx->cv.fc_w;
@@ -201,9 +206,6 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* triples, int stride,
 
 int kp_conve_features(kp_ctx* ctx, int Q, const int32_t* triples, int stride, const float* mimic, float* x_out,
                       cudaStream_t st) {
-  return kp_conve_features_ex(ctx, Q, triples, stride, mimic, x_out, nullptr, st);
+  return kp_conve_features_ex(ctx, Q, triples, triples + 1, stride, mimic, nullptr, x_out, nullptr, st);
 }
 
-int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch*, const kp_hp*, cudaStream_t) {
-  KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE post-training is not built yet");
-}

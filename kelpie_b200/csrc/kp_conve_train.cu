@@ -1,0 +1,308 @@
+// Batched ConvE mimic post-training (KelpieBCEOptimizer, bce_optimizer.py:161-208;
+// extract_batch :98-112; ConvE.all_scores conve.py:133-158; BCELoss; Adam lr = 1e-3).
+// SURVEY.md section 9.4 gives the arithmetic.
+//
+// A step of one candidate covers up to `batch_size` (lhs, rel) pairs:
+//   * "A" pairs (lhs == mimic): x = phi(e_M, R[r]) is recomputed every step; one fused
+//     score->sigmoid->contract pass gives O = sum_j sigmoid(z_j) E_j over the frozen entities,
+//     hence d loss / d x = (O + s_M e_M - sum_j t_j E_j) / (B (N+1)) without the dense
+//     [B, N+1] prediction / target matrices; it is pulled back through the frozen network
+//     (BN3 -> Linear^T -> ReLU/BN2 -> Conv^T -> BN1) to the lhs half of the stacked input.
+//   * "B" pairs (frozen lhs, the mimic is their only positive): x is computed once per
+//     batch; they reach e_M only through score column M.
+// Dropout (conve.py:34-36, active during post-training, model.py:114-125) is supported for
+// rate 0 only in this build.
+#include "kp_flash.cuh"
+#include "kp_internal.h"
+#include "kp_plan.cuh"
+
+namespace {
+
+constexpr int CT = 256;
+constexpr int BQ = 4;  // slots per CTA in the backward kernel (share every fc_w read)
+
+__device__ __forceinline__ float blk_sum(float v, float* red) {
+  __syncthreads();
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  float s = 0.f;
+#pragma unroll
+  for (int w = 0; w < CT / 32; ++w) s += red[w];
+  return s;
+}
+
+struct CvDx {
+  int GA, N, D, n_strips;
+  float ta, tb;  // target = ta * [j in positives] + tb
+  const float* ent;
+  const float* colsum;
+  const float* bn3;
+  const int32_t *a_cand, *a_pair;
+  const int32_t *nA, *nB;
+  const int64_t* pos_off;
+  const int32_t* pos_ids;
+  const float* xA;
+  const float* pO;
+  const float* mim;
+  float* dh;       // [GA, D] gradient at the Linear output
+  float* colcoef;  // [GA]
+};
+
+__global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
+  extern __shared__ float dsm[];
+  __shared__ float red[CT / 32];
+  const int g = blockIdx.x, tid = threadIdx.x, D = p.D;
+  float* acc = dsm;  // [D]
+  const int c = p.a_cand[g];
+  const float* eM = p.mim + (size_t)c * D;
+  const float* x = p.xA + (size_t)g * D;
+  float part = 0.f;
+  for (int k = tid; k < D; k += CT) part = __fmaf_rn(x[k], eM[k], part);
+  const float zM = blk_sum(part, red);
+  const float sM = 1.f / (1.f + expf(-zM));
+  const int pair = p.a_pair[g];
+  const int64_t pb = p.pos_off[pair], pe = p.pos_off[pair + 1];
+  bool m_pos = false;
+  for (int64_t i = pb; i < pe; ++i) m_pos |= (p.pos_ids[i] == p.N);
+  const float scale = 1.f / ((float)(p.nA[c] + p.nB[c]) * (float)(p.N + 1));
+  for (int k = tid; k < D; k += CT) {
+    float o = 0.f;
+    for (int s = 0; s < p.n_strips; ++s) o += p.pO[((size_t)s * p.GA + g) * D + k];
+    float tsum = 0.f;
+    for (int64_t i = pb; i < pe; ++i) {
+      const int e = p.pos_ids[i];
+      tsum += (e == p.N) ? eM[k] : p.ent[(size_t)e * D + k];
+    }
+    const float dx = (o + sM * eM[k] - p.ta * tsum - p.tb * (p.colsum[k] + eM[k])) * scale;
+    const float a3 = p.bn3[k] / sqrtf(p.bn3[3 * D + k] + 1e-5f);
+    p.dh[(size_t)g * D + k] = (x[k] > 0.f) ? dx * a3 : 0.f;
+  }
+  if (tid == 0) p.colcoef[g] = (sM - (p.ta * (m_pos ? 1.f : 0.f) + p.tb)) * scale;
+}
+
+struct CvBack {
+  int GA, D, H, F, hidden;
+  const float *fc_w, *conv_w, *bn1, *bn2;
+  const float* feat;  // [GA, hidden] post-ReLU feature maps saved by the forward kernel
+  const float* dh;    // [GA, D]
+  float* glhs;        // [GA, D] gradient w.r.t. the lhs embedding
+};
+
+__global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
+  extern __shared__ float bsm[];
+  const int D = p.D, H = p.H, W2 = H - 2, hidden = p.hidden, per_f = 38 * W2;
+  float* dh = bsm;              // [BQ][D]
+  float* dcv = dh + BQ * D;     // [BQ][hidden]
+  const int tid = threadIdx.x, g0 = blockIdx.x * BQ;
+  for (int i = tid; i < BQ * D; i += CT) {
+    const int qb = i / D, k = i % D;
+    dh[i] = (g0 + qb < p.GA) ? p.dh[(size_t)(g0 + qb) * D + k] : 0.f;
+  }
+  __syncthreads();
+  // Linear^T, then ReLU / BN2 backward
+  for (int i = tid; i < hidden; i += CT) {
+    float acc[BQ];
+#pragma unroll
+    for (int qb = 0; qb < BQ; ++qb) acc[qb] = 0.f;
+    for (int k = 0; k < D; ++k) {
+      const float w = p.fc_w[(size_t)k * hidden + i];
+#pragma unroll
+      for (int qb = 0; qb < BQ; ++qb) acc[qb] = __fmaf_rn(w, dh[qb * D + k], acc[qb]);
+    }
+    const int c = i / per_f;
+    const float a2 = p.bn2[c] / sqrtf(p.bn2[3 * p.F + c] + 1e-5f);
+#pragma unroll
+    for (int qb = 0; qb < BQ; ++qb) {
+      const bool on = (g0 + qb < p.GA) && p.feat[(size_t)(g0 + qb) * hidden + i] > 0.f;
+      dcv[qb * hidden + i] = on ? acc[qb] * a2 : 0.f;
+    }
+  }
+  __syncthreads();
+  // Conv^T restricted to the lhs half of the 40 x H image, then BN1 backward
+  const float a1 = p.bn1[0] / sqrtf(p.bn1[3] + 1e-5f);
+  for (int i = tid; i < BQ * D; i += CT) {
+    const int qb = i / D, k = i % D, y = k / H, x = k % H;
+    if (g0 + qb >= p.GA) continue;
+    const float* dc = dcv + qb * hidden;
+    float acc = 0.f;
+    for (int c = 0; c < p.F; ++c) {
+      const float* w = p.conv_w + c * 9;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y - dy;
+        if (yy < 0 || yy >= 38) continue;
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const int xx = x - dx;
+          if (xx < 0 || xx >= W2) continue;
+          acc = __fmaf_rn(w[dy * 3 + dx], dc[c * per_f + yy * W2 + xx], acc);
+        }
+      }
+    }
+    p.glhs[(size_t)(g0 + qb) * D + k] = acc * a1;
+  }
+}
+
+struct CvUpd {
+  int C, N, D;
+  long long step;
+  float lr, beta1, beta2, eps, ta, tb;
+  const int32_t *nA, *nB;
+  const int64_t *aoff, *boff;
+  const float *xA, *glhs, *colcoef, *xB;
+  float *mim, *st1, *st2;
+};
+
+__global__ void __launch_bounds__(CT) cv_update(const CvUpd p) {
+  extern __shared__ float vsm[];
+  __shared__ float red[CT / 32];
+  const int D = p.D, c = blockIdx.x, tid = threadIdx.x;
+  float* eM = vsm;
+  float* grad = eM + D;
+  const int nA = p.nA[c], nB = p.nB[c];
+  const int B = nA + nB;
+  if (B == 0) return;
+  for (int k = tid; k < D; k += CT) {
+    eM[k] = p.mim[(size_t)c * D + k];
+    grad[k] = 0.f;
+  }
+  __syncthreads();
+  for (int64_t g = p.aoff[c]; g < p.aoff[c] + nA; ++g) {
+    const float cc = p.colcoef[g];
+    for (int k = tid; k < D; k += CT) grad[k] += p.glhs[(size_t)g * D + k] + cc * p.xA[(size_t)g * D + k];
+  }
+  const float scale = 1.f / ((float)B * (float)(p.N + 1));
+  for (int64_t b = p.boff[c]; b < p.boff[c] + nB; ++b) {
+    const float* x = p.xB + (size_t)b * D;
+    float part = 0.f;
+    for (int k = tid; k < D; k += CT) part = __fmaf_rn(x[k], eM[k], part);
+    const float z = blk_sum(part, red);
+    const float coef = (1.f / (1.f + expf(-z)) - (p.ta + p.tb)) * scale;
+    for (int k = tid; k < D; k += CT) grad[k] += coef * x[k];
+  }
+  __syncthreads();
+  const double bc1 = 1.0 - pow((double)p.beta1, (double)p.step);
+  const double bc2 = 1.0 - pow((double)p.beta2, (double)p.step);
+  for (int k = tid; k < D; k += CT) {
+    const size_t idx = (size_t)c * D + k;
+    const float g = grad[k];
+    const float m = p.st1[idx] + (1.f - p.beta1) * (g - p.st1[idx]);
+    const float v = p.st2[idx] * p.beta2 + (1.f - p.beta2) * g * g;
+    p.st1[idx] = m;
+    p.st2[idx] = v;
+    const float denom = sqrtf(v) / (float)sqrt(bc2) + p.eps;
+    p.mim[idx] = eM[k] - (float)((double)p.lr / bc1) * (m / denom);
+  }
+}
+
+}  // namespace
+
+int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st) {
+  if (!b->pos || !b->pos_off || !b->pos_ids) KP_FAIL(ctx, KP_EINVAL, "ConvE post-training needs pairs and positives");
+  if (ctx->cv.drop_in != 0.f || ctx->cv.drop_fm != 0.f || ctx->cv.drop_hid != 0.f)
+    KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE post-training with dropout > 0 is not built yet (create the context with rates 0)");
+  const int C = b->n_candidates, D = ctx->D, hidden = ctx->cv.hidden;
+  const int bs = hp->batch_size, max_n = b->max_rows_per_epoch;
+  const int spe_max = max_n > 0 ? (max_n + bs - 1) / bs : 0;
+  const long long T = (long long)hp->epochs * spe_max;
+  int64_t cap = (int64_t)C * (int64_t)(max_n < bs ? max_n : bs);
+  if (b->total_rows < cap) cap = b->total_rows;
+  if (cap < 1) cap = 1;
+  if (cap > (int64_t)1 << 28) KP_FAIL(ctx, KP_EUNSUPPORTED, "batch too large (%lld pairs per step)", (long long)cap);
+  const int G = (int)cap, Gpad = ((G + 63) / 64) * 64;
+  int S = 1;
+  kp_flash_plan(ctx, 16, &S);
+
+  size_t need = 3 * WsCursor::need((size_t)C * D, 4) + 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8) +
+                6 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
+                WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
+                2 * WsCursor::need((size_t)S * G, 4) + WsCursor::need((size_t)S * G * D, 4);
+  int rc = kp_ws_reserve(ctx, need);
+  if (rc != KP_OK) return rc;
+  WsCursor ws{ctx->ws, ctx->ws + ctx->ws_bytes};
+  float* mim = ws.take<float>((size_t)C * D);
+  float* st1 = ws.take<float>((size_t)C * D);
+  float* st2 = ws.take<float>((size_t)C * D);
+  CxPlan pl;
+  pl.C = C; pl.N = (int)ctx->N; pl.D = D; pl.bs = bs; pl.epochs = hp->epochs; pl.static_epochs = 1; pl.truth_is_row = 1;
+  pl.row_off = b->row_off; pl.rows_per_epoch = b->rows_per_epoch; pl.pos = b->pos;
+  pl.nA = ws.take<int32_t>(C); pl.nB = ws.take<int32_t>(C); pl.nSelf = ws.take<int32_t>(C);
+  pl.aoff = ws.take<int64_t>(C + 1); pl.boff = ws.take<int64_t>(C + 1);
+  pl.a_cand = ws.take<int32_t>(G); pl.a_rel = ws.take<int32_t>(G); pl.a_truth = ws.take<int32_t>(G);
+  pl.b_cand = ws.take<int32_t>(G); pl.b_lhs = ws.take<int32_t>(G); pl.b_rel = ws.take<int32_t>(G);
+  float* xA = ws.take<float>((size_t)Gpad * D);
+  float* xB = ws.take<float>((size_t)Gpad * D);
+  float* feat = ws.take<float>((size_t)G * hidden);
+  float* dh = ws.take<float>((size_t)G * D);
+  float* glhs = ws.take<float>((size_t)G * D);
+  float* colcoef = ws.take<float>(G);
+  float* pm = ws.take<float>((size_t)S * G);
+  float* plv = ws.take<float>((size_t)S * G);
+  float* pO = ws.take<float>((size_t)S * G * D);
+
+  KP_CUDA(ctx, cudaMemcpyAsync(mim, b->init_rows, (size_t)C * D * 4, cudaMemcpyDeviceToDevice, st));
+  KP_CUDA(ctx, cudaMemsetAsync(st1, 0, (size_t)C * D * 4, st));
+  KP_CUDA(ctx, cudaMemsetAsync(st2, 0, (size_t)C * D * 4, st));
+
+  const float ls = hp->label_smoothing;
+  const float ta = ls != 0.f ? 1.f - ls : 1.f;
+  const float tb = ls != 0.f ? 1.f / (float)(ctx->N + 1) : 0.f;
+  const int cb = (C + 127) / 128;
+  int64_t GA = 0, GB = 0;
+  static bool configured = false;
+  const size_t back_smem = (size_t)BQ * (D + hidden) * sizeof(float);
+  if (back_smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", hidden);
+  if (!configured) {
+    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    configured = true;
+  }
+  const bool static_plan = spe_max <= 1;
+  for (long long t = 0; t < T; ++t) {
+    if (t == 0 || !static_plan) {
+      cx_count<<<cb, 128, 0, st>>>(pl, (int)t);
+      cx_scan<<<1, 1024, 0, st>>>(pl);
+      cx_assign<<<cb, 128, 0, st>>>(pl, (int)t);
+      KP_LAUNCHED(ctx, 3);
+      int64_t tot[2];
+      KP_CUDA(ctx, cudaMemcpyAsync(&tot[0], pl.aoff + C, 8, cudaMemcpyDeviceToHost, st));
+      KP_CUDA(ctx, cudaMemcpyAsync(&tot[1], pl.boff + C, 8, cudaMemcpyDeviceToHost, st));
+      KP_CUDA(ctx, cudaStreamSynchronize(st));
+      GA = tot[0];
+      GB = tot[1];
+      if (GA > G || GB > G) KP_FAIL(ctx, KP_EINVAL, "step uses more pairs than the batch declares");
+      if (GB > 0 && (rc = kp_conve_features_ex(ctx, (int)GB, pl.b_lhs, pl.b_rel, 1, nullptr, nullptr, xB, nullptr, st)) != KP_OK)
+        return rc;
+    }
+    int ns = 1;
+    if (GA > 0) {
+      if ((rc = kp_conve_features_ex(ctx, (int)GA, nullptr, pl.a_rel, 1, mim, pl.a_cand, xA, feat, st)) != KP_OK) return rc;
+      kp_flash_plan(ctx, (int)GA, &ns);
+      if ((rc = kp_flash_simt(ctx, xA, (int)GA, KP_FLASH_SIGMOID, pm, plv, pO, st)) != KP_OK) return rc;
+      CvDx d;
+      d.GA = (int)GA; d.N = (int)ctx->N; d.D = D; d.n_strips = ns; d.ta = ta; d.tb = tb;
+      d.ent = ctx->ent; d.colsum = ctx->cv.ent_colsum; d.bn3 = ctx->cv.bn3;
+      d.a_cand = pl.a_cand; d.a_pair = pl.a_truth; d.nA = pl.nA; d.nB = pl.nB;
+      d.pos_off = b->pos_off; d.pos_ids = b->pos_ids; d.xA = xA; d.pO = pO; d.mim = mim; d.dh = dh; d.colcoef = colcoef;
+      cv_dx<<<(int)GA, CT, (size_t)D * 4, st>>>(d);
+      CvBack k;
+      k.GA = (int)GA; k.D = D; k.H = ctx->cv.H; k.F = ctx->cv.n_filters; k.hidden = hidden;
+      k.fc_w = ctx->cv.fc_w; k.conv_w = ctx->cv.conv_w; k.bn1 = ctx->cv.bn1; k.bn2 = ctx->cv.bn2;
+      k.feat = feat; k.dh = dh; k.glhs = glhs;
+      cv_backward<<<(int)((GA + BQ - 1) / BQ), CT, back_smem, st>>>(k);
+      KP_LAUNCHED(ctx, 2);
+    }
+    if (GA + GB > 0) {
+      CvUpd u;
+      u.C = C; u.N = (int)ctx->N; u.D = D; u.step = t + 1;
+      u.lr = hp->lr; u.beta1 = hp->beta1; u.beta2 = hp->beta2; u.eps = hp->eps; u.ta = ta; u.tb = tb;
+      u.nA = pl.nA; u.nB = pl.nB; u.aoff = pl.aoff; u.boff = pl.boff;
+      u.xA = xA; u.glhs = glhs; u.colcoef = colcoef; u.xB = xB; u.mim = mim; u.st1 = st1; u.st2 = st2;
+      cv_update<<<C, CT, (size_t)2 * D * 4, st>>>(u);
+      KP_LAUNCHED(ctx, 1);
+    }
+  }
+  KP_CUDA(ctx, cudaMemcpyAsync(b->out_rows, mim, (size_t)C * D * 4, cudaMemcpyDeviceToDevice, st));
+  return KP_OK;
+}

@@ -129,3 +129,6 @@ int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w);
 // features x = phi(lhs, rel) for Q (lhs,rel) pairs; lhs id N -> mimic row q
 int kp_conve_features(kp_ctx* ctx, int Q, const int32_t* triples, int stride, const float* mimic,
                       float* x_out, cudaStream_t st);
+int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32_t* rel_ids, int stride,
+                         const float* mimic, const int32_t* mimic_index, float* x_out, float* feat_out,
+                         cudaStream_t st);

@@ -44,6 +44,7 @@ class HP(Structure):
 class PTBatch(Structure):
     _fields_ = [
         ("n_candidates", c_int32), ("static_epochs", c_int32),
+        ("max_rows_per_epoch", c_int32), ("reserved", c_int32), ("total_rows", c_int64),
         ("row_off", c_void_p), ("rows_per_epoch", c_void_p), ("pos", c_void_p), ("neg", c_void_p),
         ("pos_off", c_void_p), ("pos_ids", c_void_p), ("init_rows", c_void_p), ("out_rows", c_void_p),
         ("dropout_seed", c_uint64),
@@ -230,7 +231,10 @@ class Context:
             keep.append(t)
             return _ptr(t)
 
-        b = PTBatch(C, 1 if static_epochs else 0, d(row_off, torch.int64), d(rows_per_epoch, torch.int32),
+        rpe = np.asarray(rows_per_epoch.cpu() if isinstance(rows_per_epoch, torch.Tensor) else rows_per_epoch)
+        ro = np.asarray(row_off.cpu() if isinstance(row_off, torch.Tensor) else row_off)
+        b = PTBatch(C, 1 if static_epochs else 0, int(rpe.max()) if len(rpe) else 0, 0, int(ro[-1]),
+                    d(row_off, torch.int64), d(rows_per_epoch, torch.int32),
                     d(pos, torch.int32), d(neg, torch.int32), d(pos_off, torch.int64), d(pos_ids, torch.int32),
                     _ptr(init), _ptr(out), int(dropout_seed))
         self._check(self.lib.kp_post_train_batch(self.handle, ctypes.byref(b), ctypes.byref(hp), self._stream()),

@@ -10,7 +10,7 @@ from tests.golden_util import load, seed_all, trace_of
 pytestmark = pytest.mark.gpu
 
 RTOL = 1e-4
-READY = {"TransE": True, "ComplEx": False, "ConvE": False}
+READY = {"TransE": True, "ComplEx": True, "ConvE": True}
 
 
 def _dataset(z):
