@@ -174,8 +174,14 @@ int kp_post_train_batch(kp_ctx* ctx, const kp_pt_batch* batch, const kp_hp* hp, 
 int64_t kp_launch_count(const kp_ctx* ctx);
 
 /* Set a tuning / debugging knob ("force_simt" = 1 routes GEMM-shaped passes through the
- * CUDA-core kernels, used by the tests to cross-check the tcgen05 path). */
+ * CUDA-core kernels, used by the tests to cross-check the tcgen05 path; "timing" = 1 brackets
+ * the library's kernels with CUDA events, see kp_stat). */
 int kp_set_option(kp_ctx* ctx, const char* name, int64_t value);
+
+/* Per-category device time of the library's own kernels, measured with CUDA events on the
+ * launching stream while option "timing" is 1.  name = "ms_<cat>" | "n_<cat>" | "reset" with
+ * cat in {pass, flash, transe_train, update, conv}.  Synchronises the recorded events. */
+int kp_stat(kp_ctx* ctx, const char* name, double* out);
 
 #ifdef __cplusplus
 }

@@ -28,7 +28,42 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->force_simt = value;
     return KP_OK;
   }
+  if (!strcmp(name, "timing")) {
+    ctx->timing = value;
+    return KP_OK;
+  }
   KP_FAIL(ctx, KP_EINVAL, "unknown option '%s'", name);
+}
+
+static int drain_timers(kp_ctx* ctx) {
+  for (auto& t : ctx->timed) {
+    KP_CUDA(ctx, cudaEventSynchronize(t.b));
+    float ms = 0.f;
+    KP_CUDA(ctx, cudaEventElapsedTime(&ms, t.a, t.b));
+    ctx->t_ms[t.cat] += ms;
+    ctx->t_n[t.cat] += 1;
+    cudaEventDestroy(t.a);
+    cudaEventDestroy(t.b);
+  }
+  ctx->timed.clear();
+  return KP_OK;
+}
+
+extern "C" int kp_stat(kp_ctx* ctx, const char* name, double* out) {
+  if (!ctx || !name || !out) return KP_EINVAL;
+  static const char* cats[] = {"pass", "flash", "transe_train", "update", "conv"};
+  int rc = drain_timers(ctx);
+  if (rc != KP_OK) return rc;
+  if (!strcmp(name, "reset")) {
+    for (int i = 0; i < kp_ctx::T_NCAT; ++i) ctx->t_ms[i] = 0, ctx->t_n[i] = 0;
+    *out = 0;
+    return KP_OK;
+  }
+  for (int i = 0; i < kp_ctx::T_NCAT; ++i) {
+    if (!strncmp(name, "ms_", 3) && !strcmp(name + 3, cats[i])) { *out = ctx->t_ms[i]; return KP_OK; }
+    if (!strncmp(name, "n_", 2) && !strcmp(name + 2, cats[i])) { *out = (double)ctx->t_n[i]; return KP_OK; }
+  }
+  KP_FAIL(ctx, KP_EINVAL, "unknown stat '%s'", name);
 }
 
 static bool is_device_ptr(const void* p) {
@@ -72,13 +107,19 @@ static encode_tiled_fn get_encode() {
 
 int kp_encode_2d_f32(kp_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols,
                      int64_t ld_floats, int box_rows, int box_cols, bool swizzle128) {
+  return kp_encode_2d(ctx, map, base, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, rows, cols, ld_floats, box_rows, box_cols,
+                      swizzle128);
+}
+
+int kp_encode_2d(kp_ctx* ctx, CUtensorMap* map, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                 int64_t rows, int64_t cols, int64_t ld_floats, int box_rows, int box_cols, bool swizzle128) {
   encode_tiled_fn enc = get_encode();
   if (!enc) KP_FAIL(ctx, KP_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld_floats * 4};
+  cuuint64_t strides[1] = {(cuuint64_t)ld_floats * (cuuint64_t)elem_bytes};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides,
+  CUresult r = enc(map, dtype, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swizzle128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_NONE,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -88,16 +129,20 @@ int kp_encode_2d_f32(kp_ctx* ctx, CUtensorMap* map, const float* base, int64_t r
   return KP_OK;
 }
 
-int kp_ws_reserve(kp_ctx* ctx, size_t bytes) {
-  if (bytes <= ctx->ws_bytes) return KP_OK;
+int kp_ws_reserve(kp_ctx* ctx, size_t bytes, int arena) {
+  if (bytes <= ctx->ws_arena_bytes[arena]) return KP_OK;
   // grow-only; the old block is kept until destroy (in-flight kernels may still read it)
   size_t want = bytes + (bytes >> 2) + (1 << 20);
   void* d = nullptr;
   cudaError_t e = cudaMalloc(&d, want);
   if (e != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "workspace cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
   ctx->owned.push_back(d);
-  ctx->ws = static_cast<char*>(d);
-  ctx->ws_bytes = want;
+  ctx->ws_arena[arena] = static_cast<char*>(d);
+  ctx->ws_arena_bytes[arena] = want;
+  if (arena == 0) {
+    ctx->ws = ctx->ws_arena[0];
+    ctx->ws_bytes = want;
+  }
   return KP_OK;
 }
 

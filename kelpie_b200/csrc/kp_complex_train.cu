@@ -208,9 +208,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
   if (cap > (int64_t)1 << 30) KP_FAIL(ctx, KP_EUNSUPPORTED, "batch too large (%lld rows per step)", (long long)cap);
   const int G = (int)cap;
   const int Gpad = ((G + 63) / 64) * 64;
-  int n_strips = 1;
-  kp_flash_plan(ctx, 16, &n_strips);  // worst case (few rows -> many strips)
-  const int S = n_strips > 64 ? 64 : n_strips;
+  const int S = kp_flash_max_strips(ctx);  // worst case (few rows -> many strips)
 
   size_t need = 0;
   need += 3 * WsCursor::need((size_t)C * D, 4);         // mim, st1, st2
@@ -261,8 +259,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       cx_build_queries<<<(int)((GB + 7) / 8), 256, 0, st>>>((int)GB, D, ctx->ent, ctx->rel, nullptr, nullptr, pl.b_lhs, pl.b_rel, qB);
       KP_LAUNCHED(ctx, 1);
       int ns = 1;
-      kp_flash_plan(ctx, (int)GB, &ns);
-      int r2 = kp_flash_simt(ctx, qB, (int)GB, KP_FLASH_SOFTMAX, pm, plv, pO, st);
+      int r2 = kp_flash_run(ctx, qB, (int)GB, KP_FLASH_SOFTMAX, pm, plv, pO, st, &ns);
       if (r2 != KP_OK) return r2;
       cx_lse<<<(int)((GB + 255) / 256), 256, 0, st>>>((int)GB, ns, pm, plv, lseB);
       KP_LAUNCHED(ctx, 1);
@@ -278,8 +275,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
     if (GA > 0) {
       cx_build_queries<<<(int)((GA + 7) / 8), 256, 0, st>>>((int)GA, D, ctx->ent, ctx->rel, mim, pl.a_cand, nullptr, pl.a_rel, qA);
       KP_LAUNCHED(ctx, 1);
-      kp_flash_plan(ctx, (int)GA, &ns);
-      if ((rc = kp_flash_simt(ctx, qA, (int)GA, KP_FLASH_SOFTMAX, pm, plv, pO, st)) != KP_OK) return rc;
+      if ((rc = kp_flash_run(ctx, qA, (int)GA, KP_FLASH_SOFTMAX, pm, plv, pO, st, &ns)) != KP_OK) return rc;
     }
     if (GA + GB > 0) {
       CxUpd u;

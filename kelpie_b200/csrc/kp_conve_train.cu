@@ -212,8 +212,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   if (cap < 1) cap = 1;
   if (cap > (int64_t)1 << 28) KP_FAIL(ctx, KP_EUNSUPPORTED, "batch too large (%lld pairs per step)", (long long)cap);
   const int G = (int)cap, Gpad = ((G + 63) / 64) * 64;
-  int S = 1;
-  kp_flash_plan(ctx, 16, &S);
+  const int S = kp_flash_max_strips(ctx);
 
   size_t need = 3 * WsCursor::need((size_t)C * D, 4) + 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8) +
                 6 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
@@ -278,8 +277,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
     int ns = 1;
     if (GA > 0) {
       if ((rc = kp_conve_features_ex(ctx, (int)GA, nullptr, pl.a_rel, 1, mim, pl.a_cand, xA, feat, st)) != KP_OK) return rc;
-      kp_flash_plan(ctx, (int)GA, &ns);
-      if ((rc = kp_flash_simt(ctx, xA, (int)GA, KP_FLASH_SIGMOID, pm, plv, pO, st)) != KP_OK) return rc;
+      if ((rc = kp_flash_run(ctx, xA, (int)GA, KP_FLASH_SIGMOID, pm, plv, pO, st, &ns)) != KP_OK) return rc;
       CvDx d;
       d.GA = (int)GA; d.N = (int)ctx->N; d.D = D; d.n_strips = ns; d.ta = ta; d.tb = tb;
       d.ent = ctx->ent; d.colsum = ctx->cv.ent_colsum; d.bn3 = ctx->cv.bn3;

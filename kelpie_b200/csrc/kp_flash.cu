@@ -225,6 +225,7 @@ int kp_flash_simt(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
       KP_CUDA(ctx, cudaFuncSetAttribute(flash_simt_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); \
       configured = true;                                                                                           \
     }                                                                                                              \
+    KpTimer timer(ctx, kp_ctx::T_FLASH, st);                                                                        \
     flash_simt_kernel<V><<<grid, FTHREADS, smem, st>>>(p);                                                         \
   }
   if (ov <= 2) KP_FLASH_CASE(2)
@@ -236,4 +237,21 @@ int kp_flash_simt(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
 #undef KP_FLASH_CASE
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
+}
+
+int kp_flash_max_strips(kp_ctx* ctx) {
+  int a = 1, b = 1;
+  kp_flash_plan(ctx, 16, &a);
+  kp_flash_umma_plan(ctx, 32, &b);
+  return a > b ? a : b;
+}
+
+int kp_flash_run(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
+                 cudaStream_t st, int* n_strips) {
+  if (kp_flash_umma_usable(ctx, G)) {
+    kp_flash_umma_plan(ctx, G, n_strips);
+    return kp_flash_umma(ctx, qmat, G, mode, part_m, part_l, part_O, st);
+  }
+  kp_flash_plan(ctx, G, n_strips);
+  return kp_flash_simt(ctx, qmat, G, mode, part_m, part_l, part_O, st);
 }

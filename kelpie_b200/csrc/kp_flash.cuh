@@ -10,6 +10,17 @@ int kp_flash_plan(kp_ctx* ctx, int G, int* n_strips);
 int kp_flash_simt(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
                   cudaStream_t st);
 
+// tcgen05 version (kp_flash_umma.cu): same contract, used for >= 32 rows and D <= 512
+bool kp_flash_umma_usable(kp_ctx* ctx, int G);
+int kp_flash_umma_plan(kp_ctx* ctx, int G, int* n_strips);
+int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
+                  cudaStream_t st);
+// Dispatcher: runs the pass on the tensor cores when usable, else on CUDA cores; returns the
+// number of strips written.  kp_flash_max_strips bounds it for buffer sizing.
+int kp_flash_run(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
+                 cudaStream_t st, int* n_strips);
+int kp_flash_max_strips(kp_ctx* ctx);
+
 #ifdef __CUDACC__
 // Merge the per-strip softmax statistics of row g: returns M = max_s m_s and L = sum_s l_s e^{m_s-M}.
 __device__ __forceinline__ void kp_flash_merge_stats(const float* part_m, const float* part_l, int n_strips, int G,

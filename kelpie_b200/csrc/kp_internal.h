@@ -37,13 +37,30 @@ struct kp_ctx {
     float drop_in = 0, drop_fm = 0, drop_hid = 0;
   } cv;
 
-  // grow-only device workspace arena
+  // split bf16 entity tables for the tcgen05 passes (built on first use, kp_flash_umma.cu)
+  struct {
+    bool ready = false;
+    void *ent_hi = nullptr, *ent_lo = nullptr;
+    CUtensorMap eh_map, el_map;
+  } um;
+
+  // grow-only device workspace arenas (0: drivers' scratch, 1: the tcgen05 pass's own scratch)
   std::vector<void*> owned;
-  char* ws = nullptr;
+  char* ws = nullptr;  // == ws_arena[0]
   size_t ws_bytes = 0;
+  char* ws_arena[2] = {nullptr, nullptr};
+  size_t ws_arena_bytes[2] = {0, 0};
 
   int64_t launches = 0;
   int64_t force_simt = 0;
+
+  // optional per-category kernel timing (kp_set_option("timing", 1); read with kp_stat)
+  enum { T_PASS = 0, T_FLASH = 1, T_TRANSE_TRAIN = 2, T_UPDATE = 3, T_CONV = 4, T_NCAT = 5 };
+  int64_t timing = 0;
+  struct Timed { cudaEvent_t a, b; int cat; };
+  std::vector<Timed> timed;
+  double t_ms[T_NCAT] = {0, 0, 0, 0, 0};
+  int64_t t_n[T_NCAT] = {0, 0, 0, 0, 0};
   std::string err;
 };
 
@@ -73,8 +90,28 @@ struct kp_ctx {
   } while (0)
 
 void kp_set_error(kp_ctx* ctx, const char* msg);
+// CUDA-event bracket around a kernel launch on its own stream (no-op unless timing is on)
+struct KpTimer {
+  kp_ctx* ctx;
+  cudaStream_t st;
+  bool on;
+  kp_ctx::Timed t;
+  KpTimer(kp_ctx* c, int cat, cudaStream_t s) : ctx(c), st(s), on(c->timing != 0) {
+    if (!on) return;
+    t.cat = cat;
+    if (cudaEventCreate(&t.a) != cudaSuccess || cudaEventCreate(&t.b) != cudaSuccess) { on = false; return; }
+    cudaEventRecord(t.a, st);
+  }
+  ~KpTimer() {
+    if (!on) return;
+    cudaEventRecord(t.b, st);
+    ctx->timed.push_back(t);
+  }
+};
 // workspace: returns a 1024B-aligned device pointer valid until the next kp_ws_reset
-int kp_ws_reserve(kp_ctx* ctx, size_t bytes);
+int kp_ws_reserve(kp_ctx* ctx, size_t bytes, int arena = 0);
+int kp_encode_2d(kp_ctx* ctx, CUtensorMap* map, const void* base, CUtensorMapDataType dtype, int elem_bytes,
+                 int64_t rows, int64_t cols, int64_t ld_elems, int box_rows, int box_cols, bool swizzle128);
 int kp_encode_2d_f32(kp_ctx* ctx, CUtensorMap* map, const float* base, int64_t rows, int64_t cols,
                      int64_t ld_floats, int box_rows, int box_cols, bool swizzle128);
 

@@ -241,6 +241,7 @@ int launch(kp_ctx* ctx, const CUtensorMap& qmap, const PassK& p, dim3 grid, cuda
     KP_CUDA(ctx, cudaFuncSetAttribute(pass_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured = true;
   }
+  KpTimer timer(ctx, kp_ctx::T_PASS, st);
   pass_kernel<OP><<<grid, N_THREADS, SMEM_BYTES, st>>>(ctx->ent_map, qmap, p);
   KP_LAUNCHED(ctx, 1);
   return KP_OK;

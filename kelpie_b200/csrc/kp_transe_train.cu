@@ -194,6 +194,7 @@ int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cud
   p.hp = *hp;
   const size_t smem = (size_t)(3 + TT_WARPS) * ctx->D * sizeof(float);
   const int vpl = (ctx->D + 127) / 128;
+  KpTimer timer(ctx, kp_ctx::T_TRANSE_TRAIN, st);
   if (vpl <= 1) {
     transe_train_kernel<1><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 2) {

@@ -20,7 +20,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkelpie_
 
 EXPORTS = [
     "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
-    "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option",
+    "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
 ]
 
 
@@ -86,6 +86,8 @@ def load_library():
     lib.kp_launch_count.restype = c_int64
     lib.kp_set_option.argtypes = [c_void_p, c_char_p, c_int64]
     lib.kp_set_option.restype = c_int
+    lib.kp_stat.argtypes = [c_void_p, c_char_p, POINTER(ctypes.c_double)]
+    lib.kp_stat.restype = c_int
     _lib = lib
     return lib
 
@@ -180,6 +182,12 @@ class Context:
 
     def set_option(self, name, value):
         self._check(self.lib.kp_set_option(self.handle, name.encode(), int(value)), "kp_set_option")
+
+    def stat(self, name):
+        """Per-category kernel time / launch count measured by the library (option "timing")."""
+        out = ctypes.c_double()
+        self._check(self.lib.kp_stat(self.handle, name.encode(), ctypes.byref(out)), "kp_stat")
+        return out.value
 
     def upload_filter(self, to_filter):
         keys, off, ids = filter_csr(to_filter, self.R2)

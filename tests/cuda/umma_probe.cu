@@ -1,0 +1,130 @@
+// Stand-alone probe of the tcgen05 building blocks used by kp_flash_umma.cu:
+//   case 0: D[128,N] = A[128,K] * B[N,K]^T        A, B K-major, 128B swizzle (TMA-loaded)
+//   case 1: D[128,N] = A[128,K] * Bt[K,N]         B MN-major (rows of Bt are K, N contiguous)
+// bf16 inputs, fp32 accumulate in TMEM, read back with tcgen05.ld.  Prints max |err|.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <vector>
+#include <cmath>
+#include "../../kelpie_b200/csrc/kp_ptx.cuh"
+
+#define CK(x) do { cudaError_t e = (x); if (e != cudaSuccess) { printf("CUDA error %s at %d\n", cudaGetErrorString(e), __LINE__); exit(2);} } while (0)
+
+typedef CUresult (*enc_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                           const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                           CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static enc_fn get_enc() {
+  void* p = nullptr; cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+  return (enc_fn)p;
+}
+static CUtensorMap make_map(void* base, int rows, int cols, int box_rows, int box_cols) {
+  CUtensorMap m; cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows}; cuuint64_t str[1] = {(cuuint64_t)cols * 2};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows}; cuuint32_t es[2] = {1, 1};
+  CUresult r = get_enc()(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, str, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { printf("encode failed %d\n", (int)r); exit(2); }
+  return m;
+}
+
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+// K = 128 (two 64-wide k-blocks).  mode 0: B K-major [N rows x K]; mode 1: B MN-major [K rows x N]
+template <int N>
+__global__ void probe(const __grid_constant__ CUtensorMap amap, const __grid_constant__ CUtensorMap bmap, int mode, float* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sA = sm;                  // 2 k-blocks x [128 x 128B] = 32 KB
+  uint8_t* sB = sm + 32768;          // mode 0: 2 k-blocks x [N x 128B]; mode 1: (N/64) boxes x [128 k-rows x 128B]
+  __shared__ uint64_t full, done;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { ptx::mbar_init(&full, 1); ptx::mbar_init(&done, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base, 256); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  if (threadIdx.x == 0) {
+    uint32_t bytes = 32768 + (mode == 0 ? 2 * N * 128 : (N / 64) * 128 * 128);
+    ptx::mbar_arrive_expect_tx(&full, bytes);
+    for (int kb = 0; kb < 2; ++kb) ptx::tma_load_2d(sA + kb * 16384, &amap, &full, kb * 64, 0);
+    if (mode == 0) for (int kb = 0; kb < 2; ++kb) ptx::tma_load_2d(sB + kb * N * 128, &bmap, &full, kb * 64, 0);
+    else for (int nb = 0; nb < N / 64; ++nb) ptx::tma_load_2d(sB + nb * 16384, &bmap, &full, nb * 64, 0);
+    ptx::mbar_wait(&full, 0);
+    ptx::tc_fence_after();
+    uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (mode == 1) idesc |= (1u << 16);  // B is MN-major
+    for (int ks = 0; ks < 8; ++ks) {     // 8 x K16
+      const int kb = ks >> 2, kk = ks & 3;
+      uint64_t ad = make_desc(ptx::smem_u32(sA + kb * 16384) + kk * 32, 16, 1024);
+      uint64_t bd;
+      if (mode == 0) bd = make_desc(ptx::smem_u32(sB + kb * N * 128) + kk * 32, 16, 1024);
+      else bd = make_desc(ptx::smem_u32(sB) + ks * 2048, 16384, 1024);  // 16 k-rows per step; LBO = next 64-wide N box
+      ptx::umma_bf16(tm, ad, bd, idesc, ks > 0);
+    }
+    ptx::umma_commit(&done);
+  }
+  __syncthreads();
+  ptx::mbar_wait(&done, 0);
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16) + c0, r);
+    ptx::tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[(warp * 32 + lane) * N + c0 + i] = __uint_as_float(r[i]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tm, 256);
+}
+
+template <int N>
+static double run(int mode) {
+  const int M = 128, K = 128;
+  std::vector<__nv_bfloat16> A(M * K), B(N * K), Bt(K * N);
+  std::vector<float> Af(M * K), Bf(N * K);
+  srand(1234 + mode + N);
+  for (int i = 0; i < M * K; ++i) { float v = (rand() % 2001 - 1000) / 1000.f; A[i] = __float2bfloat16(v); Af[i] = __bfloat162float(A[i]); }
+  for (int n = 0; n < N; ++n) for (int k = 0; k < K; ++k) { float v = (rand() % 2001 - 1000) / 1000.f; __nv_bfloat16 b = __float2bfloat16(v); B[n * K + k] = b; Bt[k * N + n] = b; Bf[n * K + k] = __bfloat162float(b); }
+  __nv_bfloat16 *dA, *dB; float* dO;
+  CK(cudaMalloc(&dA, M * K * 2)); CK(cudaMalloc(&dB, N * K * 2)); CK(cudaMalloc(&dO, M * N * 4));
+  CK(cudaMemcpy(dA, A.data(), M * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, mode == 0 ? B.data() : Bt.data(), N * K * 2, cudaMemcpyHostToDevice));
+  CUtensorMap am = make_map(dA, M, K, 128, 64);
+  CUtensorMap bm = mode == 0 ? make_map(dB, N, K, N, 64) : make_map(dB, K, N, 128, 64);
+  CK(cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+  probe<N><<<1, 128, 100 * 1024>>>(am, bm, mode, dO);
+  CK(cudaDeviceSynchronize());
+  std::vector<float> O(M * N);
+  CK(cudaMemcpy(O.data(), dO, M * N * 4, cudaMemcpyDeviceToHost));
+  double err = 0;
+  for (int m = 0; m < M; ++m) for (int n = 0; n < N; ++n) {
+    double ref = 0; for (int k = 0; k < K; ++k) ref += (double)Af[m * K + k] * Bf[n * K + k];
+    err = fmax(err, fabs(ref - O[m * N + n]));
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dO);
+  return err;
+}
+
+int main() {
+  int bad = 0;
+  double e;
+  e = run<64>(0);  printf("K-major  N=64  max_err=%g\n", e); bad += e > 1e-3;
+  e = run<128>(0); printf("K-major  N=128 max_err=%g\n", e); bad += e > 1e-3;
+  e = run<64>(1);  printf("MN-major N=64  max_err=%g\n", e); bad += e > 1e-3;
+  e = run<128>(1); printf("MN-major N=128 max_err=%g\n", e); bad += e > 1e-3;
+  printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
+  return bad ? 1 : 0;
+}

@@ -1,0 +1,76 @@
+"""tcgen05 fused pass vs the CUDA-core pass (option force_simt) and vs the oracle, at sizes where
+the tensor-core path is taken (>= 32 query rows per step)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _kg(seed, N, R, deg):
+    rng = np.random.default_rng(seed)
+    return rng, N, R, deg
+
+
+def _facts(rng, N, R, T):
+    """T facts of the mimic (id N): random direction, relation and neighbour."""
+    out = []
+    for _ in range(T):
+        x, r = int(rng.integers(0, N)), int(rng.integers(0, R))
+        out.append((N, r, x) if rng.random() < 0.5 else (x, r, N))
+    return out
+
+
+def _run(kind, ctx, hp, jobs, N, R, force_simt):
+    from kelpie_b200 import plans, runtime
+    ctx.set_option("force_simt", 1 if force_simt else 0)
+    torch.manual_seed(0)
+    np.random.seed(0)
+    batch = plans.Batch(kind, N, R, hp)
+    for facts, init in jobs:
+        batch.add(facts, init)
+    rows = ctx.post_train(runtime.make_hp(kind, hp), **batch.arrays())
+    torch.cuda.synchronize()
+    return rows.cpu().numpy()
+
+
+@pytest.mark.parametrize("dim", [64, 200, 256])
+def test_complex_post_train_umma_matches_simt_and_oracle(dim):
+    from kelpie_b200 import runtime
+    from oracle import kelpie_oracle as ko
+    rng = np.random.default_rng(dim)
+    N, R, D = 3001, 7, 2 * dim
+    ent = (rng.standard_normal((N, D)) * 0.25).astype(np.float32)
+    rel = (rng.standard_normal((2 * R, D)) * 0.25).astype(np.float32)
+    hp = dict(optimizer_name="Adagrad", batch_size=512, epochs=6, lr=0.043, decay1=0.9, decay2=0.999,
+              regularizer_name="N3", regularizer_weight=0)
+    jobs = [(_facts(rng, N, R, int(rng.integers(3, 12))), (rng.random(D) * 1e-3).astype(np.float32)) for _ in range(40)]
+    ctx = runtime.Context("ComplEx", ent, rel)
+    simt = _run("ComplEx", ctx, hp, jobs, N, R, True)
+    umma = _run("ComplEx", ctx, hp, jobs, N, R, False)
+    scale = np.abs(simt).max(axis=1, keepdims=True)
+    assert (np.abs(umma - simt) / scale).max() < 1e-4  # stated tolerance: 1e-4 relative to the row's max |.|
+    # oracle on three of the jobs
+    kg = ko.KG(np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), N, R)
+    w = ko.Weights("ComplEx", ent, rel, init_scale=1e-3)
+    for j in (0, 17, 39):
+        facts, init = jobs[j]
+        table = ko.post_train(w, kg, torch.from_numpy(init).view(1, -1), facts, hp)
+        ref = table[-1].numpy()
+        assert np.abs(umma[j] - ref).max() < 1e-4 * np.abs(ref).max()
+
+
+def test_conve_post_train_umma_matches_simt():
+    from kelpie_b200 import runtime
+    from tests.golden_util import load
+    z, meta, kg, w, order = load("ConvE")
+    rng = np.random.default_rng(5)
+    N, R, D = int(z["n_ent"]), int(z["n_rel"]), 80
+    conve = {k: v for k, v in w.conve.items()}
+    ctx = runtime.Context("ConvE", z["w_ent"], z["w_rel"], conve=conve)
+    hp = dict(batch_size=512, label_smoothing=0.1, lr=0.018, decay=0.995, epochs=5)
+    jobs = [(_facts(rng, N, R, int(rng.integers(4, 10))), rng.random(D).astype(np.float32)) for _ in range(24)]
+    simt = _run("ConvE", ctx, hp, jobs, N, R, True)
+    umma = _run("ConvE", ctx, hp, jobs, N, R, False)
+    scale = np.abs(simt).max(axis=1, keepdims=True)
+    assert (np.abs(umma - simt) / scale).max() < 1e-4
