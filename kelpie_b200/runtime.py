@@ -225,7 +225,7 @@ class Context:
         return (ts, bs, rk, cn) if counters else (ts, bs, rk)
 
     def post_train(self, hp, init_rows, row_off, rows_per_epoch, pos, neg=None, pos_off=None, pos_ids=None,
-                   static_epochs=False, dropout_seed=0):
+                   static_epochs=False, dropout_seed=0, max_rows_per_epoch=None, total_rows=None):
         """Run one batch of C mimic post-trainings; returns the [C, D] post-trained rows (device)."""
         init = self.dev(init_rows, torch.float32).view(-1, self.D)
         C = init.shape[0]
@@ -239,9 +239,13 @@ class Context:
             keep.append(t)
             return _ptr(t)
 
-        rpe = np.asarray(rows_per_epoch.cpu() if isinstance(rows_per_epoch, torch.Tensor) else rows_per_epoch)
-        ro = np.asarray(row_off.cpu() if isinstance(row_off, torch.Tensor) else row_off)
-        b = PTBatch(C, 1 if static_epochs else 0, int(rpe.max()) if len(rpe) else 0, 0, int(ro[-1]),
+        if max_rows_per_epoch is None:  # host-known totals (pass them explicitly to avoid a device read)
+            rpe = np.asarray(rows_per_epoch.cpu() if isinstance(rows_per_epoch, torch.Tensor) else rows_per_epoch)
+            max_rows_per_epoch = int(rpe.max()) if len(rpe) else 0
+        if total_rows is None:
+            ro = np.asarray(row_off.cpu() if isinstance(row_off, torch.Tensor) else row_off)
+            total_rows = int(ro[-1])
+        b = PTBatch(C, 1 if static_epochs else 0, int(max_rows_per_epoch), 0, int(total_rows),
                     d(row_off, torch.int64), d(rows_per_epoch, torch.int32),
                     d(pos, torch.int32), d(neg, torch.int32), d(pos_off, torch.int64), d(pos_ids, torch.int32),
                     _ptr(init), _ptr(out), int(dropout_seed))

@@ -1,0 +1,181 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, the host-side
+mirrors (dataset overlay, batch plans, filter CSR) agree with the oracle, and the candidate
+sharding works across two gloo ranks.  No kernel is launched here."""
+import ctypes
+import os
+import re
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import kelpie_oracle as ko
+from tests.golden_util import load, seed_all
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    from kelpie_b200 import runtime
+    lib = runtime.load_library()
+    header = open(os.path.join(ROOT, "include", "kelpie_b200.h")).read()
+    declared = set(re.findall(r"\b(kp_[a-z_0-9]+)\s*\(", header))
+    assert declared == set(runtime.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.kp_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    """Without a CUDA device context creation fails loudly with KP_ECUDA (no CPU path)."""
+    from kelpie_b200 import runtime
+    if torch.cuda.is_available():
+        pytest.skip("needs a machine without a GPU")
+    lib = runtime.load_library()
+    ent = np.zeros((8, 8), np.float32)
+    h = ctypes.c_void_p()
+    rc = lib.kp_ctx_create(0, 0, 8, 4, 8, 2, ent.ctypes.data, ent.ctypes.data, None, ctypes.byref(h))
+    assert rc == -2 and b"no CUDA device" in lib.kp_last_error(None)
+    with pytest.raises(RuntimeError):
+        runtime.Context("TransE", ent, ent)
+
+
+def test_struct_layouts_match_header():
+    from kelpie_b200 import runtime
+    assert ctypes.sizeof(runtime.HP) == 40
+    assert ctypes.sizeof(runtime.PTBatch) == 96
+    assert ctypes.sizeof(runtime.ConvEWeights) == 7 * 8 + 5 * 4 + 4
+
+
+@pytest.mark.parametrize("kind", ["TransE", "ComplEx", "ConvE"])
+def test_batch_plans_match_oracle_draws(kind):
+    """plans.Batch consumes the generators exactly like the oracle (hence the reference)."""
+    from kelpie_b200 import plans
+    z, meta, kg, w, order = load(kind)
+    hp = meta["hp"]
+    N, R = kg.num_entities, kg.num_relations
+    e = next(iter(order))
+    facts = [ko._swap(t, e, N) for t in order[e]]
+    seed_all(7)
+    log = []
+    ko.post_train(w, kg, torch.rand(1, w.dim), facts, hp, log)
+    seed_all(7)
+    torch.rand(1, w.dim)
+    b = plans.Batch(kind, N, R, hp)
+    b.add(facts, np.zeros(w.dim, np.float32))
+    a = b.arrays()
+    if kind == "TransE":
+        pos = np.concatenate([s["pos"] for s in log])
+        neg = np.concatenate([s["neg"] for s in log])
+        np.testing.assert_array_equal(a["pos"], pos)
+        np.testing.assert_array_equal(a["neg"], neg)
+    elif kind == "ComplEx":
+        assert a["static_epochs"]
+        got = sorted(map(tuple, a["pos"]))
+        for s in log:  # every step covers the same multiset of rows
+            assert sorted(map(tuple, s["rows"])) == got
+        assert torch.rand(1).item() == pytest.approx(_after(kind, w, kg, facts, hp))
+    else:
+        np.testing.assert_array_equal(a["pos"][:, :2], log[0]["pairs"])
+
+
+def _after(kind, w, kg, facts, hp):
+    seed_all(7)
+    ko.post_train(w, kg, torch.rand(1, w.dim), facts, hp)
+    return torch.rand(1).item()
+
+
+def test_kelpie_dataset_overlay_matches_oracle_mimic():
+    from kelpie_b200.data import Dataset, KelpieDataset
+    z, meta, kg, w, order = load("TransE")
+    ds = Dataset("g", z["train"], z["valid"], z["test"], kg.num_entities, kg.num_relations)
+    e = next(iter(order))
+    ds.entity_to_training_triples[e] = order[e]
+    kd = KelpieDataset(ds, e)
+    mim = ko.Mimic(kg, e, order[e])
+    assert [tuple(t) for t in kd.kelpie_training_triples] == mim.base_facts
+    rule = [order[e][0], order[e][2]]
+    kd.remove_training_triples(rule)
+    facts, flt = mim.without(rule)
+    assert [tuple(t) for t in kd.kelpie_training_triples] == facts
+    for key, v in flt.items():
+        if key[0] == mim.M:
+            assert sorted(kd.to_filter[key]) == sorted(v)
+    kd.undo_removal()
+    assert [tuple(t) for t in kd.kelpie_training_triples] == mim.base_facts
+    for key, v in mim.filter.items():
+        if key[0] == mim.M:
+            assert sorted(kd.to_filter[key]) == sorted(v)
+    kd.add_training_triples(rule[:1])
+    facts, flt = mim.with_added(rule[:1])
+    assert [tuple(t) for t in kd.kelpie_training_triples] == facts
+    kd.undo_addition()
+    # the dataset's own dicts were never touched
+    assert all(kg.to_filter[k] == list(ds.to_filter[k]) for k in kg.to_filter)
+
+
+def test_filter_csr_is_sorted_and_deduplicated():
+    from kelpie_b200.runtime import filter_csr
+    keys, off, ids = filter_csr({(3, 1): [5, 2, 5], (0, 2): [7], (3, 0): []}, 4)
+    np.testing.assert_array_equal(keys, [2, 13])
+    np.testing.assert_array_equal(off, [0, 1, 3])
+    np.testing.assert_array_equal(ids, [7, 2, 5])
+
+
+def test_dataset_mirror_matches_oracle_kg():
+    from kelpie_b200.data import Dataset
+    z, meta, kg, w, order = load("ComplEx")
+    ds = Dataset("g", z["train"], z["valid"], z["test"], kg.num_entities, kg.num_relations)
+    assert ds.relation_to_type == kg.relation_to_type
+    for e in range(0, kg.num_entities, 17):
+        assert set(ds.entity_to_training_triples[e]) == set(kg.facts_of[e])
+        assert ds.entity_to_degree.get(e, 0) == kg.degree.get(e, 0)
+    np.testing.assert_array_equal(ds.invert_triples(z["test"][:5]), kg.invert(z["test"][:5]))
+
+
+def test_shard_bounds_balance_and_cover():
+    from kelpie_b200.parallel import shard_bounds
+    costs = [1, 9, 1, 1, 4, 4, 10, 2]
+    b = shard_bounds(costs, 4)
+    assert b[0] == 0 and b[-1] == len(costs) and all(x <= y for x, y in zip(b, b[1:]))
+    assert shard_bounds([], 3) == [0, 0, 0, 0]
+    assert shard_bounds([5], 2)[-1] == 1
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import torch, torch.distributed as dist
+from kelpie_b200.parallel import ShardedEngine
+
+class FakeEngine:  # MockEngine pattern of the reference's builder tests (test_stochastic_builder.py:7-11)
+    def compute_relevances(self, pred, rules):
+        return [float(sum(t[2] for t in r)) + 0.5 for r in rules]
+
+dist.init_process_group("gloo")
+rules = [[(1, 0, i)] * (1 + i % 3) for i in range(11)]
+got = ShardedEngine(FakeEngine()).compute_relevances((1, 0, 2), rules)
+want = FakeEngine().compute_relevances((1, 0, 2), rules)
+assert got == want, (got, want)
+dist.barrier()
+dist.destroy_process_group()
+print("ok", dist.is_initialized())
+'''
+
+
+def test_sharded_engine_two_gloo_ranks(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=120)
+        assert p.returncode == 0, out
