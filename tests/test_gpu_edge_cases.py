@@ -1,0 +1,151 @@
+"""Edge cases of the post-training kernels against the oracle on identical draws: multi-step
+epochs (rows > batch_size), mixed static / per-epoch batches, L1 TransE, empty candidates,
+self-loop facts, ragged batches; plus size-independent properties of the rank kernel."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import kelpie_oracle as ko
+from tests.golden_util import load, seed_all
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-4  # mimic rows: max |diff| <= RTOL * max |row|
+
+
+def _ctx(kind, z, w, norm=2):
+    from kelpie_b200 import runtime
+    conve = dict(w.conve) if kind == "ConvE" else None
+    return runtime.Context(kind, z["w_ent"], z["w_rel"], norm=norm, conve=conve)
+
+
+def _both(kind, z, w, kg, hp, jobs, ctx):
+    """Oracle rows and CUDA rows for the same jobs, same generator state."""
+    from kelpie_b200 import plans, runtime
+    N, R = kg.num_entities, kg.num_relations
+    seed_all(11)
+    want = []
+    for facts, init in jobs:
+        table = ko.post_train(w, kg, torch.from_numpy(init).view(1, -1), facts, hp)
+        want.append(table[-1].numpy())
+    seed_all(11)
+    b = plans.Batch(kind, N, R, hp)
+    for facts, init in jobs:
+        b.add(facts, init)
+    got = ctx.post_train(runtime.make_hp(kind, hp), **b.arrays()).cpu().numpy()
+    return got, np.stack(want)
+
+
+def _jobs(rng, N, R, D, sizes, scale):
+    out = []
+    for T in sizes:
+        facts = []
+        for _ in range(T):
+            x, r = int(rng.integers(0, N)), int(rng.integers(0, R))
+            facts.append((N, r, x) if rng.random() < 0.5 else (x, r, N))
+        out.append((facts, (rng.random(D) * scale).astype(np.float32)))
+    return out
+
+
+def _assert_rows(got, want):
+    scale = np.maximum(np.abs(want).max(axis=1, keepdims=True), 1e-30)
+    assert (np.abs(got - want) / scale).max() <= RTOL
+
+
+@pytest.mark.parametrize("norm", [1, 2])
+def test_transe_multi_step_ragged_and_empty(norm):
+    z, meta, kg, w, order = load("TransE")
+    w.norm = norm
+    hp = dict(meta["hp"], batch_size=4, epochs=7)  # 2T > batch_size -> several dependent steps per epoch
+    rng = np.random.default_rng(3)
+    jobs = _jobs(rng, kg.num_entities, kg.num_relations, w.dim, [0, 1, 2, 5, 9, 3], 0.3)
+    jobs[3][0][0] = (kg.num_entities, 1, kg.num_entities)  # self-loop fact (M, r, M)
+    got, want = _both("TransE", z, w, kg, hp, jobs, _ctx("TransE", z, w, norm))
+    np.testing.assert_array_equal(got[0], jobs[0][1])  # no facts: init row untouched
+    _assert_rows(got, want)
+
+
+def test_complex_multi_step_and_mixed_batches():
+    z, meta, kg, w, order = load("ComplEx")
+    hp = dict(meta["hp"], batch_size=6, epochs=5)  # jobs with 2T <= 6 are static, the others permuted per epoch
+    rng = np.random.default_rng(4)
+    jobs = _jobs(rng, kg.num_entities, kg.num_relations, w.dim, [0, 2, 3, 7, 10, 1], 1e-3)
+    jobs[4][0][1] = (kg.num_entities, 2, kg.num_entities)
+    got, want = _both("ComplEx", z, w, kg, hp, jobs, _ctx("ComplEx", z, w))
+    np.testing.assert_array_equal(got[0], jobs[0][1])
+    _assert_rows(got, want)
+
+
+@pytest.mark.parametrize("opt", ["Adam", "SGD"])
+def test_complex_other_optimizers_and_n3(opt):
+    z, meta, kg, w, order = load("ComplEx")
+    hp = dict(meta["hp"], optimizer_name=opt, lr=0.01, epochs=4, regularizer_weight=0.05)
+    rng = np.random.default_rng(5)
+    jobs = _jobs(rng, kg.num_entities, kg.num_relations, w.dim, [3, 6], 0.2)
+    got, want = _both("ComplEx", z, w, kg, hp, jobs, _ctx("ComplEx", z, w))
+    _assert_rows(got, want)
+
+
+def test_conve_multi_step_pairs():
+    z, meta, kg, w, order = load("ConvE")
+    hp = dict(meta["hp"], batch_size=3, epochs=4)  # pairs > batch_size -> several steps per epoch
+    rng = np.random.default_rng(6)
+    jobs = _jobs(rng, kg.num_entities, kg.num_relations, w.dim, [0, 4, 6, 2], 1.0)
+    got, want = _both("ConvE", z, w, kg, hp, jobs, _ctx("ConvE", z, w))
+    np.testing.assert_array_equal(got[0], jobs[0][1])
+    _assert_rows(got, want)
+
+
+@pytest.mark.parametrize("kind", ["TransE", "ComplEx", "ConvE"])
+def test_rank_kernel_properties(kind):
+    """Size-independent properties: the fused rank equals a count over the materialised scores,
+    filtering never worsens a rank, and filtering everything leaves rank 1."""
+    from kelpie_b200 import runtime
+    z, meta, kg, w, order = load(kind)
+    ctx = _ctx(kind, z, w)
+    N = kg.num_entities
+    rng = np.random.default_rng(8)
+    Q = 150
+    triples = np.stack([rng.integers(0, N, Q), rng.integers(0, 2 * kg.num_relations, Q), rng.integers(0, N, Q)], 1)
+    sc = ctx.all_scores(triples)
+    t = sc.gather(1, torch.as_tensor(triples[:, 2], device=sc.device).view(-1, 1))
+    better = (sc < t) if kind == "TransE" else (sc > t)
+    ties = (sc == t)
+    empty = np.zeros(Q + 1, dtype=np.int64)
+    ts, bs, rk, cnt = ctx.filtered_rank(triples, runtime.RANK_MODEL, flt_off=empty, counters=True)
+    assert torch.equal(cnt[:, 0].long(), better.sum(1))
+    assert torch.equal(rk, better.sum(1) + ties.sum(1))  # ties (incl. the target itself) count against
+    torch.testing.assert_close(ts, t.view(-1), rtol=1e-5, atol=1e-6)
+    # random filters (ragged, some empty): rank can only improve
+    lens = rng.integers(0, 40, Q)
+    off = np.zeros(Q + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    ids = np.concatenate([np.sort(rng.choice(N, n, replace=False)) for n in lens]).astype(np.int32)
+    _, _, rk_f = ctx.filtered_rank(triples, runtime.RANK_MODEL, flt_off=off, flt_ids=ids)
+    assert bool((rk_f <= rk).all())
+    # everything filtered: only the (restored) target remains
+    allids = np.tile(np.arange(N, dtype=np.int32), Q)
+    off_all = np.arange(Q + 1, dtype=np.int64) * N
+    _, _, rk_all = ctx.filtered_rank(triples, runtime.RANK_MODEL, flt_off=off_all, flt_ids=allids)
+    assert bool((rk_all == 1).all())
+
+
+def test_post_training_is_deterministic_and_batch_order_independent():
+    from kelpie_b200 import plans, runtime
+    z, meta, kg, w, order = load("ComplEx")
+    ctx = _ctx("ComplEx", z, w)
+    hp = dict(meta["hp"], epochs=5)
+    rng = np.random.default_rng(9)
+    jobs = _jobs(rng, kg.num_entities, kg.num_relations, w.dim, [3, 5, 8, 2, 6, 4, 7, 9] * 6, 1e-3)
+
+    def run(js):
+        b = plans.Batch("ComplEx", kg.num_entities, kg.num_relations, hp)
+        for f, i in js:
+            b.add(f, i)
+        return ctx.post_train(runtime.make_hp("ComplEx", hp), **b.arrays()).cpu().numpy()
+
+    a = run(jobs)
+    np.testing.assert_array_equal(a, run(jobs))          # idempotent / deterministic
+    perm = rng.permutation(len(jobs))
+    b = run([jobs[i] for i in perm])
+    scale = np.abs(a).max(axis=1, keepdims=True)
+    assert (np.abs(b - a[perm]) / scale[perm]).max() < 1e-5  # a candidate does not depend on its neighbours
