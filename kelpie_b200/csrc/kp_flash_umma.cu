@@ -9,13 +9,20 @@
 // same 4 bytes per element in HBM); query rows and the probabilities P are split on the fly.
 //
 // One CTA = 128 query rows x one strip of 128-entity tiles x one chunk of <= 256 output dims:
-//   warp 0      TMA producer (4-slot ring of 32 KB {hi,lo} boxes of [128 rows x 64 dims])
-//   warp 1      MMA issuer   S = Q E^T  (M128 N128, K-major A/B)      -> TMEM S[2]
-//                            O += P E   (M128 N64,  A = P K-major from smem, B = E MN-major)
+//   warp 0      TMA producer (6-slot ring of 32 KB {hi,lo} boxes of [128 rows x 64 dims])
+//   warp 1      MMA issuer   S = Q E^T  (M128 N128, K-major A/B from smem)   -> TMEM S[2]
+//                            O += P E   (M128 N64,  A = P from TMEM, B = E MN-major from smem)
 //   warps 2..5  one thread per query row: TMEM S -> online softmax (lazy rescale of O in
-//               TMEM) or sigmoid -> P split into bf16 hi/lo, written to smem in the
-//               128B-swizzled K-major layout the MMA reads
+//               TMEM) or sigmoid -> P split into bf16 hi/lo and written back to TMEM over the
+//               S columns it was computed from (no shared-memory round trip for P)
 // PV of tile i-1 is issued behind S of tile i so the softmax of a tile overlaps tensor work.
+//
+// Thread-block clusters: the CTAs of `cq` neighbouring query tiles x all dim chunks form one
+// cluster and walk the same entity tiles in lock step.  Every operand box is fetched from L2 by
+// ONE CTA of its sharer set and TMA-multicast into the same ring slot of every sharer (entity
+// boxes of the S phase: all CTAs; query boxes: the CTAs of that query tile; entity boxes of the
+// PV phase: the CTAs of that dim chunk); a slot is re-used once every CTA of the cluster has
+// released it (tcgen05.commit multicast onto all `empty` barriers).
 #include <cuda_bf16.h>
 
 #include "kp_flash.cuh"
@@ -26,21 +33,21 @@ namespace {
 
 constexpr int UT = 192;               // threads
 constexpr int SLOT = 32768;           // {hi 16 KB | lo 16 KB}
-constexpr int NSLOT = 4;
-constexpr int P_BYTES = 65536;        // Ph[2][16 KB] | Pl[2][16 KB]
+constexpr int NSLOT = 6;
 constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_TAU = 8.0f;   // rescale O only when the row max grew by more than this
 
 struct UCtl {
   uint64_t full[NSLOT], empty[NSLOT];
-  uint64_t s_full[2], s_empty[2];
-  uint64_t p_full, p_empty, o_done;
+  uint64_t s_full[2];
+  uint64_t p_full, pv_done, o_done;
   uint32_t tmem_base;
 };
-constexpr size_t U_SMEM = (size_t)NSLOT * SLOT + P_BYTES + sizeof(UCtl) + 1024;
+constexpr size_t U_SMEM = (size_t)NSLOT * SLOT + sizeof(UCtl) + 1024;
 
 struct UK {
   int G, N, D, KB, n_tiles, tiles_per_strip, boxes_per_chunk, mode;
+  int cq;  // query tiles per cluster (cluster = cq query tiles x all dim chunks)
   float* part_m;
   float* part_l;
   float* part_O;
@@ -66,8 +73,7 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
   extern __shared__ uint8_t uraw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(uraw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = sm;
-  uint8_t* Pbuf = sm + (size_t)NSLOT * SLOT;
-  UCtl* ctl = reinterpret_cast<UCtl*>(Pbuf + P_BYTES);
+  UCtl* ctl = reinterpret_cast<UCtl*>(sm + (size_t)NSLOT * SLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int strip = blockIdx.x, qtile = blockIdx.y, chunk = blockIdx.z;
@@ -75,20 +81,24 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
   const int t1 = min(t0 + p.tiles_per_strip, p.n_tiles);
   const int ntile = t1 - t0;
   const int box0 = chunk * p.boxes_per_chunk;
-  const int nbox = min(p.boxes_per_chunk, p.KB - box0);
-  if (ntile <= 0 || nbox <= 0) return;
+  const int nbox = p.boxes_per_chunk;  // identical for every chunk (tables are zero-padded)
+  if (ntile <= 0) return;              // uniform over the cluster (same strip)
+  const uint32_t csize = ptx::cluster_nctarank(), crank = ptx::cluster_ctarank();
+  const uint32_t cq = (uint32_t)p.cq, cc = csize / cq;
+  const uint32_t qsel = crank % cq, csel = crank / cq;
+  const uint16_t mask_all = (uint16_t)((1u << csize) - 1);
+  uint16_t mask_q = 0, mask_c = 0;  // CTAs sharing my query tile / my dim chunk
+  for (uint32_t c = 0; c < cc; ++c) mask_q |= (uint16_t)(1u << (qsel + cq * c));
+  for (uint32_t q = 0; q < cq; ++q) mask_c |= (uint16_t)(1u << (q + cq * csel));
 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
-      ptx::mbar_init(&ctl->empty[s], 1);
+      ptx::mbar_init(&ctl->empty[s], csize);
     }
-    for (int b = 0; b < 2; ++b) {
-      ptx::mbar_init(&ctl->s_full[b], 1);
-      ptx::mbar_init(&ctl->s_empty[b], 128);
-    }
+    for (int b = 0; b < 2; ++b) ptx::mbar_init(&ctl->s_full[b], 1);
     ptx::mbar_init(&ctl->p_full, 128);
-    ptx::mbar_init(&ctl->p_empty, 1);
+    ptx::mbar_init(&ctl->pv_done, 1);
     ptx::mbar_init(&ctl->o_done, 1);
     ptx::fence_barrier_init();
   }
@@ -98,9 +108,13 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) ptx::cluster_sync_all();  // barriers of every CTA initialised before any remote arrive
   ptx::tc_fence_after();
   const uint32_t tm = ctl->tmem_base;
-  const uint32_t TM_O = tm, TM_S = tm + 256;  // O: cols [0,256)   S[b]: cols [256 + 128 b, +128)
+  // O: cols [0,256).  S[b]: cols [256 + 128 b, +128); after the softmax the same columns hold P:
+  // for every 32-column chunk c, cols [32c, +16) = bf16x2-packed hi and [32c+16, +16) = lo of the
+  // 32 entities of that chunk (MMA K-step ks reads 8 packed columns at 32 (ks/2) + 8 (ks%2) (+16)).
+  const uint32_t TM_O = tm, TM_S = tm + 256;
 
   if (warp == 0) {
     // ------------------------------- TMA producer -------------------------------
@@ -109,23 +123,37 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
       ptx::prefetch_tmap(&el_map);
       ptx::prefetch_tmap(&qh_map);
       ptx::prefetch_tmap(&ql_map);
-      uint32_t use = 0;
-      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row) {
+      uint32_t use = 0, n_q = 0, n_es = 0, n_pv = 0;
+      // every CTA arms its own `full` barrier; only the issuer of the sharer set fetches the box
+      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row, bool issue, uint16_t mask) {
         const int s = use % NSLOT;
         ptx::mbar_wait(&ctl->empty[s], ((use / NSLOT) & 1) ^ 1);
         ptx::mbar_arrive_expect_tx(&ctl->full[s], SLOT);
-        ptx::tma_load_2d(ring + (size_t)s * SLOT, hi, &ctl->full[s], col, row);
-        ptx::tma_load_2d(ring + (size_t)s * SLOT + 16384, lo, &ctl->full[s], col, row);
+        if (issue) {
+          uint8_t* dst = ring + (size_t)s * SLOT;
+          if (csize == 1) {
+            ptx::tma_load_2d(dst, hi, &ctl->full[s], col, row);
+            ptx::tma_load_2d(dst + 16384, lo, &ctl->full[s], col, row);
+          } else {
+            ptx::tma_load_2d_mc(dst, hi, &ctl->full[s], col, row, mask);
+            ptx::tma_load_2d_mc(dst + 16384, lo, &ctl->full[s], col, row, mask);
+          }
+        }
         ++use;
       };
       for (int i = 0; i <= ntile; ++i) {
         if (i < ntile)
           for (int kb = 0; kb < p.KB; ++kb) {
-            load(&qh_map, &ql_map, kb * 64, qtile * 128);
-            load(&eh_map, &el_map, kb * 64, (t0 + i) * 128);
+            load(&qh_map, &ql_map, kb * 64, qtile * 128, csel == (n_q % cc), mask_q);
+            ++n_q;
+            load(&eh_map, &el_map, kb * 64, (t0 + i) * 128, crank == (n_es % csize), mask_all);
+            ++n_es;
           }
         if (i > 0)
-          for (int b = 0; b < nbox; ++b) load(&eh_map, &el_map, (box0 + b) * 64, (t0 + i - 1) * 128);
+          for (int b = 0; b < nbox; ++b) {
+            load(&eh_map, &el_map, (box0 + b) * 64, (t0 + i - 1) * 128, qsel == (n_pv % cq), mask_c);
+            ++n_pv;
+          }
       }
     }
   } else if (warp == 1) {
@@ -133,9 +161,15 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
     if (lane == 0) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
-      const uint32_t ring_a = ptx::smem_u32(ring), p_a = ptx::smem_u32(Pbuf);
+      const uint32_t ring_a = ptx::smem_u32(ring);
       uint32_t use = 0;
       auto wait_slot = [&](uint32_t u) { ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1); };
+      auto release = [&](uint32_t u) {  // slot free in THIS CTA once the MMAs issued so far have read it
+        if (csize == 1)
+          ptx::umma_commit(&ctl->empty[u % NSLOT]);
+        else
+          ptx::umma_commit_mc(&ctl->empty[u % NSLOT], mask_all);
+      };
       auto pv = [&](int t) {
         ptx::mbar_wait(&ctl->p_full, t & 1);
         ptx::tc_fence_after();
@@ -144,23 +178,23 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
           ptx::tc_fence_after();
           const uint32_t e_hi = ring_a + (use % NSLOT) * SLOT, e_lo = e_hi + 16384;
           const uint32_t d_o = TM_O + b * 64;
+          const uint32_t p_t = TM_S + (t & 1) * 128;
           for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t pa = (ks >> 2) * 16384 + (ks & 3) * 32;
-            const uint64_t a_hi = udesc(p_a + pa, 16, 1024), a_lo = udesc(p_a + 32768 + pa, 16, 1024);
+            const uint32_t a_hi = p_t + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
             const uint64_t b_hi = udesc(e_hi + ks * 2048, 16384, 1024), b_lo = udesc(e_lo + ks * 2048, 16384, 1024);
-            ptx::umma_bf16(d_o, a_hi, b_hi, idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
-            ptx::umma_bf16(d_o, a_hi, b_lo, idesc_pv, 1u);
-            ptx::umma_bf16(d_o, a_lo, b_hi, idesc_pv, 1u);
+            ptx::umma_bf16_ts(d_o, a_hi, b_hi, idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
+            ptx::umma_bf16_ts(d_o, a_hi, b_lo, idesc_pv, 1u);
+            ptx::umma_bf16_ts(d_o, a_lo, b_hi, idesc_pv, 1u);
           }
-          ptx::umma_commit(&ctl->empty[use % NSLOT]);
+          release(use);
           ++use;
         }
-        ptx::umma_commit(&ctl->p_empty);
+        ptx::umma_commit(&ctl->pv_done);
       };
       for (int i = 0; i < ntile; ++i) {
+        // S(i) overwrites the buffer that held P(i-2): tcgen05.mma executes in issue order, and
+        // PV(i-2) (its last reader) was issued before, so no extra barrier is needed here.
         const int sb = i & 1;
-        ptx::mbar_wait(&ctl->s_empty[sb], ((i >> 1) & 1) ^ 1);
-        ptx::tc_fence_after();
         const uint32_t d_s = TM_S + sb * 128;
         for (int kb = 0; kb < p.KB; ++kb) {
           wait_slot(use);
@@ -175,8 +209,8 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
             ptx::umma_bf16(d_s, a_hi, b_lo, idesc_s, 1u);
             ptx::umma_bf16(d_s, a_lo, b_hi, idesc_s, 1u);
           }
-          ptx::umma_commit(&ctl->empty[use % NSLOT]);
-          ptx::umma_commit(&ctl->empty[(use + 1) % NSLOT]);
+          release(use);
+          release(use + 1);
           use += 2;
         }
         ptx::umma_commit(&ctl->s_full[sb]);
@@ -218,29 +252,15 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
           m_ref = mx;
         }
       }
-      // the previous tile's P has been consumed and O is up to date
-      ptx::mbar_wait(&ctl->p_empty, (i & 1) ^ 1);
-      ptx::tc_fence_after();
-      if (__any_sync(0xffffffffu, factor != 1.f)) {
-#pragma unroll 1
-        for (int c0 = 0; c0 < ocols; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
-          ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
-        }
-        ptx::tmem_st_wait();
-      }
+      // P(i) = exp(S - m_ref) (or sigmoid), split into bf16 hi/lo and written over the S chunk it
+      // came from; this overlaps PV(i-1) and S(i+1) on the tensor pipe.
       float sum = 0.f;
       const float mneg = (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
 #pragma unroll 1
       for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r[32];
+        uint32_t r[32], w[32];
         ptx::tmem_ld_32x32(s_addr + c0, r);
         ptx::tmem_ld_wait();
-        uint32_t hi[16], lo[16];
 #pragma unroll
         for (int c = 0; c < 32; c += 2) {
           float pv[2];
@@ -256,25 +276,30 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
           }
           sum += pv[0] + pv[1];
           const __nv_bfloat16 h0 = __float2bfloat16_rn(pv[0]), h1 = __float2bfloat16_rn(pv[1]);
-          hi[c >> 1] = pack_bf16(h0, h1);
-          lo[c >> 1] = pack_bf16(__float2bfloat16_rn(pv[0] - __bfloat162float(h0)),
-                                 __float2bfloat16_rn(pv[1] - __bfloat162float(h1)));
+          w[c >> 1] = pack_bf16(h0, h1);
+          w[16 + (c >> 1)] = pack_bf16(__float2bfloat16_rn(pv[0] - __bfloat162float(h0)),
+                                       __float2bfloat16_rn(pv[1] - __bfloat162float(h1)));
         }
-        // entity columns c0..c0+31 -> k-block (c0 / 64), 16-byte chunks ((c0 % 64) / 8) .. +3, swizzled by row
-        uint8_t* base = Pbuf + (c0 >> 6) * 16384 + row * 128;
-        const int ch0 = (c0 & 63) >> 3;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int phys = ((ch0 + q4) ^ (row & 7)) << 4;
-          *reinterpret_cast<uint4*>(base + phys) = make_uint4(hi[q4 * 4], hi[q4 * 4 + 1], hi[q4 * 4 + 2], hi[q4 * 4 + 3]);
-          *reinterpret_cast<uint4*>(base + 32768 + phys) = make_uint4(lo[q4 * 4], lo[q4 * 4 + 1], lo[q4 * 4 + 2], lo[q4 * 4 + 3]);
-        }
+        ptx::tmem_st_32x32(s_addr + c0, w);
       }
       l_run = l_run * factor + sum;
-      ptx::fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+      if (__any_sync(0xffffffffu, factor != 1.f)) {
+        // O holds tiles < i only once PV(i-1) has completed
+        ptx::mbar_wait(&ctl->pv_done, (i & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < ocols; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
+          ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
+        }
+      }
+      ptx::tmem_st_wait();
       ptx::tc_fence_before();
       ptx::mbar_arrive(&ctl->p_full);
-      ptx::mbar_arrive(&ctl->s_empty[sb]);
     }
     ptx::mbar_wait(&ctl->o_done, 0);
     ptx::tc_fence_after();
@@ -300,6 +325,7 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
   }
   ptx::tc_fence_before();
   __syncthreads();
+  if (csize > 1) ptx::cluster_sync_all();  // no CTA leaves while peers may still write its smem / barriers
   if (warp == 1) ptx::tmem_dealloc(tm, 512);
 }
 
@@ -332,25 +358,52 @@ bool kp_flash_umma_usable(kp_ctx* ctx, int G) {
   return !ctx->force_simt && G >= 32 && ctx->D <= 512 && ctx->D % 4 == 0;
 }
 
-int kp_flash_umma_plan(kp_ctx* ctx, int G, int* n_strips) {
-  const int KB = (ctx->D + 63) / 64;
-  const int boxes_per_chunk = KB <= 4 ? KB : (KB + 1) / 2 > 4 ? 4 : (KB + 1) / 2;
-  const int n_chunks = (KB + boxes_per_chunk - 1) / boxes_per_chunk;
-  const int n_tiles = (int)((ctx->N + 127) / 128);
+namespace {
+struct UPlan {
+  int KBs;     // 64-wide k-blocks of the S phase = ceil(D / 64)
+  int bpc;     // 64-wide output boxes per dim chunk (<= 4 : 256 TMEM columns)
+  int cc;      // dim chunks
+  int cq;      // query tiles per cluster
+  int Dpad;    // padded row width of the split tables
+  int n_qt;    // query tiles, padded to a multiple of cq
+  int n_strips, n_tiles, tps;
+};
+UPlan umma_plan(kp_ctx* ctx, int G) {
+  UPlan u;
+  u.KBs = (ctx->D + 63) / 64;
+  u.cc = u.KBs <= 4 ? 1 : 2;  // dim chunks (clustered together only when cq > 1)
+  u.bpc = (u.KBs + u.cc - 1) / u.cc;
+  u.Dpad = (u.KBs > u.bpc * u.cc ? u.KBs : u.bpc * u.cc) * 64;
   const int n_qt = (G + 127) / 128;
-  int s = ctx->sm_count / (n_qt * n_chunks);
+  // default: independent CTAs.  Measured on B200 (1M x 512, 18k rows): clusters of 2x2 with TMA
+  // multicast run at 159 TFLOP/s vs 219 without -- the per-SM shared-memory fill rate, which
+  // multicast does not lower, is the limiter, and the lock-step slot release costs more than it saves.
+  int cq = ctx->umma_cq > 0 ? (int)ctx->umma_cq : 1;
+  while (cq > 1 && n_qt < cq) cq >>= 1;
+  u.cq = cq;
+  u.n_qt = ((n_qt + cq - 1) / cq) * cq;
+  u.n_tiles = (int)((ctx->N + 127) / 128);
+  int s = ctx->sm_count / (u.n_qt * u.cc);
   if (s > 64) s = 64;
-  if (s > n_tiles) s = n_tiles;
+  if (s > u.n_tiles) s = u.n_tiles;
   if (s < 1) s = 1;
-  const int tps = (n_tiles + s - 1) / s;
-  *n_strips = (n_tiles + tps - 1) / tps;
-  return boxes_per_chunk;
+  u.tps = (u.n_tiles + s - 1) / s;
+  u.n_strips = (u.n_tiles + u.tps - 1) / u.tps;
+  return u;
+}
+}  // namespace
+
+int kp_flash_umma_plan(kp_ctx* ctx, int G, int* n_strips) {
+  const UPlan u = umma_plan(ctx, G);
+  *n_strips = u.n_strips;
+  return u.bpc;
 }
 
 int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
                   cudaStream_t st) {
   if (G <= 0) return KP_OK;
-  const int D = ctx->D, Dpad = ((D + 63) / 64) * 64;
+  const UPlan u = umma_plan(ctx, G);
+  const int D = ctx->D, Dpad = u.Dpad;
   int rc;
   if (!ctx->um.ready) {
     const long long Npad = ((ctx->N + 127) / 128) * 128;
@@ -367,7 +420,7 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
     ctx->um.ent_lo = l;
     ctx->um.ready = true;
   }
-  const long long Gpad = ((G + 127) / 128) * 128;
+  const long long Gpad = (long long)u.n_qt * 128;
   const size_t qbytes = (size_t)Gpad * Dpad * 2;
   if ((rc = kp_ws_reserve(ctx, 2 * qbytes + 2048, 1)) != KP_OK) return rc;
   __nv_bfloat16* qh = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1]);
@@ -382,25 +435,35 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   p.G = G;
   p.N = (int)ctx->N;
   p.D = D;
-  p.KB = Dpad / 64;
-  p.n_tiles = (int)((ctx->N + 127) / 128);
-  int n_strips = 1;
-  p.boxes_per_chunk = kp_flash_umma_plan(ctx, G, &n_strips);
-  p.tiles_per_strip = (p.n_tiles + n_strips - 1) / n_strips;
+  p.KB = u.KBs;
+  p.n_tiles = u.n_tiles;
+  p.boxes_per_chunk = u.bpc;
+  p.tiles_per_strip = u.tps;
   p.mode = mode;
+  p.cq = u.cq;
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;
-  const int n_chunks = (p.KB + p.boxes_per_chunk - 1) / p.boxes_per_chunk;
   static bool configured = false;
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U_SMEM));
     configured = true;
   }
-  dim3 grid(n_strips, (G + 127) / 128, n_chunks);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(u.n_strips, u.n_qt, u.cc);
+  cfg.blockDim = dim3(UT);
+  cfg.dynamicSmemBytes = U_SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 1;
+  attr[0].val.clusterDim.y = u.cq;
+  attr[0].val.clusterDim.z = u.cq > 1 ? u.cc : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
   {
     KpTimer timer(ctx, kp_ctx::T_FLASH, st);
-    flash_umma_kernel<<<grid, UT, U_SMEM, st>>>(ctx->um.eh_map, ctx->um.el_map, qh_map, ql_map, p);
+    KP_CUDA(ctx, cudaLaunchKernelEx(&cfg, flash_umma_kernel, ctx->um.eh_map, ctx->um.el_map, qh_map, ql_map, p));
   }
   KP_LAUNCHED(ctx, 1);
   return KP_OK;

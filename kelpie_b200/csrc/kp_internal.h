@@ -53,6 +53,7 @@ struct kp_ctx {
 
   int64_t launches = 0;
   int64_t force_simt = 0;
+  int64_t umma_cq = 0;  // query tiles per cluster of the tcgen05 pass (0 = automatic)
 
   // optional per-category kernel timing (kp_set_option("timing", 1); read with kp_stat)
   enum { T_PASS = 0, T_FLASH = 1, T_TRANSE_TRAIN = 2, T_UPDATE = 3, T_CONV = 4, T_NCAT = 5 };

@@ -90,6 +90,71 @@ __global__ void probe(const __grid_constant__ CUtensorMap amap, const __grid_con
   if (warp == 0) ptx::tmem_dealloc(tm, 256);
 }
 
+// A [128 x 128] bf16 held in TMEM (two bf16 per 32-bit column, lane = row), B from smem.
+// mode 2: B K-major; mode 3: B MN-major.
+template <int N>
+__global__ void probe_ts(const __nv_bfloat16* A, const __grid_constant__ CUtensorMap bmap, int mode, float* out) {
+  extern __shared__ uint8_t raw[];
+  uint8_t* sm = (uint8_t*)(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint8_t* sB = sm;
+  __shared__ uint64_t full, done;
+  __shared__ uint32_t tmem_base;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) { ptx::mbar_init(&full, 1); ptx::mbar_init(&done, 1); ptx::fence_barrier_init(); }
+  if (warp == 0) { ptx::tmem_alloc(&tmem_base, 512); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tm = tmem_base;
+  const uint32_t TA = tm + 256;  // A region: 64 columns
+  {  // every thread stores its row: 128 bf16 = 64 packed columns
+    const int row = warp * 32 + lane;
+    for (int c0 = 0; c0 < 64; c0 += 32) {
+      uint32_t r[32];
+      for (int c = 0; c < 32; ++c) {
+        const uint32_t lo = __bfloat16_as_ushort(A[row * 128 + 2 * (c0 + c)]);
+        const uint32_t hi = __bfloat16_as_ushort(A[row * 128 + 2 * (c0 + c) + 1]);
+        r[c] = lo | (hi << 16);
+      }
+      ptx::tmem_st_32x32(TA + ((uint32_t)(warp * 32) << 16) + c0, r);
+    }
+    ptx::tmem_st_wait();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (threadIdx.x == 0) {
+    uint32_t bytes = (mode == 2 ? 2 * N * 128 : (N / 64) * 128 * 128);
+    ptx::mbar_arrive_expect_tx(&full, bytes);
+    if (mode == 2) for (int kb = 0; kb < 2; ++kb) ptx::tma_load_2d(sB + kb * N * 128, &bmap, &full, kb * 64, 0);
+    else for (int nb = 0; nb < N / 64; ++nb) ptx::tma_load_2d(sB + nb * 16384, &bmap, &full, nb * 64, 0);
+    ptx::mbar_wait(&full, 0);
+    ptx::tc_fence_after();
+    uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (mode == 3) idesc |= (1u << 16);
+    for (int ks = 0; ks < 8; ++ks) {
+      const int kb = ks >> 2, kk = ks & 3;
+      uint64_t bd;
+      if (mode == 2) bd = make_desc(ptx::smem_u32(sB + kb * N * 128) + kk * 32, 16, 1024);
+      else bd = make_desc(ptx::smem_u32(sB) + ks * 2048, 16384, 1024);
+      ptx::umma_bf16_ts(tm, TA + ks * 8, bd, idesc, ks > 0);
+    }
+    ptx::umma_commit(&done);
+  }
+  __syncthreads();
+  ptx::mbar_wait(&done, 0);
+  ptx::tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 32) {
+    uint32_t r[32];
+    ptx::tmem_ld_32x32(tm + ((uint32_t)(warp * 32) << 16) + c0, r);
+    ptx::tmem_ld_wait();
+    for (int i = 0; i < 32; ++i) out[(warp * 32 + lane) * N + c0 + i] = __uint_as_float(r[i]);
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) ptx::tmem_dealloc(tm, 512);
+}
+
 template <int N>
 static double run(int mode) {
   const int M = 128, K = 128;
@@ -101,11 +166,17 @@ static double run(int mode) {
   __nv_bfloat16 *dA, *dB; float* dO;
   CK(cudaMalloc(&dA, M * K * 2)); CK(cudaMalloc(&dB, N * K * 2)); CK(cudaMalloc(&dO, M * N * 4));
   CK(cudaMemcpy(dA, A.data(), M * K * 2, cudaMemcpyHostToDevice));
-  CK(cudaMemcpy(dB, mode == 0 ? B.data() : Bt.data(), N * K * 2, cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, (mode == 0 || mode == 2) ? B.data() : Bt.data(), N * K * 2, cudaMemcpyHostToDevice));
   CUtensorMap am = make_map(dA, M, K, 128, 64);
-  CUtensorMap bm = mode == 0 ? make_map(dB, N, K, N, 64) : make_map(dB, K, N, 128, 64);
-  CK(cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-  probe<N><<<1, 128, 100 * 1024>>>(am, bm, mode, dO);
+  const bool kmajor = (mode == 0 || mode == 2);
+  CUtensorMap bm = kmajor ? make_map(dB, N, K, N, 64) : make_map(dB, K, N, 128, 64);
+  if (mode < 2) {
+    CK(cudaFuncSetAttribute(probe<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    probe<N><<<1, 128, 100 * 1024>>>(am, bm, mode, dO);
+  } else {
+    CK(cudaFuncSetAttribute(probe_ts<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    probe_ts<N><<<1, 128, 100 * 1024>>>(dA, bm, mode, dO);
+  }
   CK(cudaDeviceSynchronize());
   std::vector<float> O(M * N);
   CK(cudaMemcpy(O.data(), dO, M * N * 4, cudaMemcpyDeviceToHost));
@@ -125,6 +196,9 @@ int main() {
   e = run<128>(0); printf("K-major  N=128 max_err=%g\n", e); bad += e > 1e-3;
   e = run<64>(1);  printf("MN-major N=64  max_err=%g\n", e); bad += e > 1e-3;
   e = run<128>(1); printf("MN-major N=128 max_err=%g\n", e); bad += e > 1e-3;
+  e = run<64>(2);  printf("A-in-TMEM, B K-major  N=64  max_err=%g\n", e); bad += e > 1e-3;
+  e = run<64>(3);  printf("A-in-TMEM, B MN-major N=64  max_err=%g\n", e); bad += e > 1e-3;
+  e = run<128>(3); printf("A-in-TMEM, B MN-major N=128 max_err=%g\n", e); bad += e > 1e-3;
   printf(bad ? "PROBE FAILED\n" : "PROBE OK\n");
   return bad ? 1 : 0;
 }
