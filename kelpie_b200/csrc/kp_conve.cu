@@ -4,6 +4,7 @@
 // The entity projection x @ E^T + sigmoid is the generic all-entity pass (kp_pass.cu).
 #include "kp_internal.h"
 #include "kp_ptx.cuh"
+#include "kp_dropout.cuh"
 
 namespace {
 
@@ -21,6 +22,11 @@ struct ConvK {
   const float *conv_w, *conv_b, *fc_w, *fc_b, *bn1, *bn2, *bn3;
   float* x_out;      // [Q, D]
   float* feat_out;   // nullable [Q, hidden]: post-ReLU feature maps (kept for the backward pass)
+  // training-mode dropout (conve.py:34-36,140-152; active during post-training, model.py:114-125)
+  const int32_t* drop_ids;  // NULL = eval mode; else the pair id keying the masks of query q
+  unsigned long long seed;
+  int step;
+  float p_in, p_fm, p_hid;
 };
 
 __device__ __forceinline__ void bn_affine(const float* bn, int n, int i, float& alpha, float& beta) {
@@ -53,6 +59,7 @@ __global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK 
         v = p.rel[(size_t)r * D + (k - D)];
       }
       v = v * a1 + b1;
+      if (p.drop_ids && p.p_in > 0.f) v *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_INPUT + k, p.p_in);
     }
     img[i] = v;
   }
@@ -71,6 +78,8 @@ __global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK 
     float a2, b2;
     bn_affine(p.bn2, p.F, c, a2, b2);
     acc = fmaxf(acc * a2 + b2, 0.f);
+    if (p.drop_ids && p.p_fm > 0.f && qbase + qb < p.Q)  // Dropout2d: whole channels
+      acc *= kp_drop_scale(p.seed, p.drop_ids[qbase + qb], p.step, KP_DROP_FEATURE + c, p.p_fm);
     feat[i] = acc;
     if (p.feat_out && qbase + qb < p.Q) p.feat_out[(size_t)(qbase + qb) * p.hidden + o] = acc;
   }
@@ -100,7 +109,11 @@ __global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK 
       bn_affine(p.bn3, D, k, a3, b3);
 #pragma unroll
       for (int qb = 0; qb < CV_QB; ++qb)
-        if (qbase + qb < p.Q) p.x_out[(size_t)(qbase + qb) * D + k] = fmaxf((acc[qb] + p.fc_b[k]) * a3 + b3, 0.f);
+        if (qbase + qb < p.Q) {
+          float h = acc[qb] + p.fc_b[k];
+          if (p.drop_ids && p.p_hid > 0.f) h *= kp_drop_scale(p.seed, p.drop_ids[qbase + qb], p.step, KP_DROP_HIDDEN + k, p.p_hid);
+          p.x_out[(size_t)(qbase + qb) * D + k] = fmaxf(h * a3 + b3, 0.f);
+        }
     }
   }
 }
@@ -167,8 +180,14 @@ int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
 
 int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32_t* rel_ids, int stride,
                          const float* mimic, const int32_t* mimic_index, float* x_out, float* feat_out,
-                         cudaStream_t st) {
+                         cudaStream_t st, const int32_t* drop_ids, unsigned long long seed, int step) {
   ConvK p;
+  p.drop_ids = drop_ids;
+  p.seed = seed;
+  p.step = step;
+  p.p_in = ctx->cv.drop_in;
+  p.p_fm = ctx->cv.drop_fm;
+  p.p_hid = ctx->cv.drop_hid;
   p.Q = Q;
   p.N = (int)ctx->N;
   p.R2 = (int)ctx->R2;
@@ -199,6 +218,7 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
     configured = true;
   }
   if (smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", p.hidden);
+  KpTimer timer(ctx, kp_ctx::T_CONV, st);
   conve_features_kernel<<<(Q + CV_QB - 1) / CV_QB, CV_THREADS, smem, st>>>(p);
   KP_LAUNCHED(ctx, 1);
   return KP_OK;

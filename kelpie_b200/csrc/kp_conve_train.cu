@@ -10,11 +10,15 @@
 //     (BN3 -> Linear^T -> ReLU/BN2 -> Conv^T -> BN1) to the lhs half of the stacked input.
 //   * "B" pairs (frozen lhs, the mimic is their only positive): x is computed once per
 //     batch; they reach e_M only through score column M.
-// Dropout (conve.py:34-36, active during post-training, model.py:114-125) is supported for
-// rate 0 only in this build.
+// Dropout (conve.py:34-36, active during post-training, model.py:114-125): masks come from a
+// counter-based generator keyed by (seed, pair, step, element) (kp_dropout.cuh) and are
+// recomputed in the backward kernels; with any rate > 0 the features of the "B" pairs are
+// recomputed every step as well (the reference pushes every pair through the network with
+// fresh masks each step).
 #include "kp_flash.cuh"
 #include "kp_internal.h"
 #include "kp_plan.cuh"
+#include "kp_dropout.cuh"
 
 namespace {
 
@@ -48,6 +52,9 @@ struct CvDx {
   const float* mim;
   float* dh;       // [GA, D] gradient at the Linear output
   float* colcoef;  // [GA]
+  unsigned long long seed;
+  int step;
+  float p_hid;
 };
 
 __global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
@@ -77,7 +84,9 @@ __global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
     }
     const float dx = (o + sM * eM[k] - p.ta * tsum - p.tb * (p.colsum[k] + eM[k])) * scale;
     const float a3 = p.bn3[k] / sqrtf(p.bn3[3 * D + k] + 1e-5f);
-    p.dh[(size_t)g * D + k] = (x[k] > 0.f) ? dx * a3 : 0.f;
+    float d = (x[k] > 0.f) ? dx * a3 : 0.f;
+    if (p.p_hid > 0.f) d *= kp_drop_scale(p.seed, pair, p.step, KP_DROP_HIDDEN + k, p.p_hid);
+    p.dh[(size_t)g * D + k] = d;
   }
   if (tid == 0) p.colcoef[g] = (sM - (p.ta * (m_pos ? 1.f : 0.f) + p.tb)) * scale;
 }
@@ -85,9 +94,13 @@ __global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
 struct CvBack {
   int GA, D, H, F, hidden;
   const float *fc_w, *conv_w, *bn1, *bn2;
-  const float* feat;  // [GA, hidden] post-ReLU feature maps saved by the forward kernel
+  const float* feat;  // [GA, hidden] post-ReLU (and post-dropout) feature maps saved by the forward kernel
   const float* dh;    // [GA, D]
   float* glhs;        // [GA, D] gradient w.r.t. the lhs embedding
+  const int32_t* pair;  // [GA] pair ids keying the dropout masks
+  unsigned long long seed;
+  int step;
+  float p_in, p_fm;
 };
 
 __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
@@ -115,8 +128,10 @@ __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
     const float a2 = p.bn2[c] / sqrtf(p.bn2[3 * p.F + c] + 1e-5f);
 #pragma unroll
     for (int qb = 0; qb < BQ; ++qb) {
-      const bool on = (g0 + qb < p.GA) && p.feat[(size_t)(g0 + qb) * hidden + i] > 0.f;
-      dcv[qb * hidden + i] = on ? acc[qb] * a2 : 0.f;
+      const bool on = (g0 + qb < p.GA) && p.feat[(size_t)(g0 + qb) * hidden + i] > 0.f;  // dropped channels are 0
+      float d = on ? acc[qb] * a2 : 0.f;
+      if (on && p.p_fm > 0.f) d *= kp_drop_scale(p.seed, p.pair[g0 + qb], p.step, KP_DROP_FEATURE + c, p.p_fm);
+      dcv[qb * hidden + i] = d;
     }
   }
   __syncthreads();
@@ -141,6 +156,7 @@ __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
         }
       }
     }
+    if (p.p_in > 0.f) acc *= kp_drop_scale(p.seed, p.pair[g0 + qb], p.step, KP_DROP_INPUT + k, p.p_in);
     p.glhs[(size_t)(g0 + qb) * D + k] = acc * a1;
   }
 }
@@ -201,8 +217,8 @@ __global__ void __launch_bounds__(CT) cv_update(const CvUpd p) {
 
 int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st) {
   if (!b->pos || !b->pos_off || !b->pos_ids) KP_FAIL(ctx, KP_EINVAL, "ConvE post-training needs pairs and positives");
-  if (ctx->cv.drop_in != 0.f || ctx->cv.drop_fm != 0.f || ctx->cv.drop_hid != 0.f)
-    KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE post-training with dropout > 0 is not built yet (create the context with rates 0)");
+  const bool dropout = ctx->cv.drop_in != 0.f || ctx->cv.drop_fm != 0.f || ctx->cv.drop_hid != 0.f;
+  const unsigned long long seed = b->dropout_seed;
   const int C = b->n_candidates, D = ctx->D, hidden = ctx->cv.hidden;
   const int bs = hp->batch_size, max_n = b->max_rows_per_epoch;
   const int spe_max = max_n > 0 ? (max_n + bs - 1) / bs : 0;
@@ -215,7 +231,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   const int S = kp_flash_max_strips(ctx);
 
   size_t need = 3 * WsCursor::need((size_t)C * D, 4) + 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8) +
-                6 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
+                7 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
                 WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
                 2 * WsCursor::need((size_t)S * G, 4) + WsCursor::need((size_t)S * G * D, 4);
   int rc = kp_ws_reserve(ctx, need);
@@ -230,7 +246,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   pl.nA = ws.take<int32_t>(C); pl.nB = ws.take<int32_t>(C); pl.nSelf = ws.take<int32_t>(C);
   pl.aoff = ws.take<int64_t>(C + 1); pl.boff = ws.take<int64_t>(C + 1);
   pl.a_cand = ws.take<int32_t>(G); pl.a_rel = ws.take<int32_t>(G); pl.a_truth = ws.take<int32_t>(G);
-  pl.b_cand = ws.take<int32_t>(G); pl.b_lhs = ws.take<int32_t>(G); pl.b_rel = ws.take<int32_t>(G);
+  pl.b_cand = ws.take<int32_t>(G); pl.b_lhs = ws.take<int32_t>(G); pl.b_rel = ws.take<int32_t>(G); pl.b_row = ws.take<int32_t>(G);
   float* xA = ws.take<float>((size_t)Gpad * D);
   float* xB = ws.take<float>((size_t)Gpad * D);
   float* feat = ws.take<float>((size_t)G * hidden);
@@ -271,23 +287,31 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
       GA = tot[0];
       GB = tot[1];
       if (GA > G || GB > G) KP_FAIL(ctx, KP_EINVAL, "step uses more pairs than the batch declares");
-      if (GB > 0 && (rc = kp_conve_features_ex(ctx, (int)GB, pl.b_lhs, pl.b_rel, 1, nullptr, nullptr, xB, nullptr, st)) != KP_OK)
+      if (GB > 0 && !dropout &&
+          (rc = kp_conve_features_ex(ctx, (int)GB, pl.b_lhs, pl.b_rel, 1, nullptr, nullptr, xB, nullptr, st)) != KP_OK)
         return rc;
     }
+    if (GB > 0 && dropout &&  // fresh masks every step for the frozen-lhs pairs too
+        (rc = kp_conve_features_ex(ctx, (int)GB, pl.b_lhs, pl.b_rel, 1, nullptr, nullptr, xB, nullptr, st, pl.b_row, seed, (int)t)) != KP_OK)
+      return rc;
     int ns = 1;
     if (GA > 0) {
-      if ((rc = kp_conve_features_ex(ctx, (int)GA, nullptr, pl.a_rel, 1, mim, pl.a_cand, xA, feat, st)) != KP_OK) return rc;
+      if ((rc = kp_conve_features_ex(ctx, (int)GA, nullptr, pl.a_rel, 1, mim, pl.a_cand, xA, feat, st,
+                                     dropout ? pl.a_truth : nullptr, seed, (int)t)) != KP_OK)
+        return rc;
       if ((rc = kp_flash_run(ctx, xA, (int)GA, KP_FLASH_SIGMOID, pm, plv, pO, st, &ns)) != KP_OK) return rc;
       CvDx d;
       d.GA = (int)GA; d.N = (int)ctx->N; d.D = D; d.n_strips = ns; d.ta = ta; d.tb = tb;
       d.ent = ctx->ent; d.colsum = ctx->cv.ent_colsum; d.bn3 = ctx->cv.bn3;
       d.a_cand = pl.a_cand; d.a_pair = pl.a_truth; d.nA = pl.nA; d.nB = pl.nB;
       d.pos_off = b->pos_off; d.pos_ids = b->pos_ids; d.xA = xA; d.pO = pO; d.mim = mim; d.dh = dh; d.colcoef = colcoef;
+      d.seed = seed; d.step = (int)t; d.p_hid = ctx->cv.drop_hid;
       cv_dx<<<(int)GA, CT, (size_t)D * 4, st>>>(d);
       CvBack k;
       k.GA = (int)GA; k.D = D; k.H = ctx->cv.H; k.F = ctx->cv.n_filters; k.hidden = hidden;
       k.fc_w = ctx->cv.fc_w; k.conv_w = ctx->cv.conv_w; k.bn1 = ctx->cv.bn1; k.bn2 = ctx->cv.bn2;
       k.feat = feat; k.dh = dh; k.glhs = glhs;
+      k.pair = pl.a_truth; k.seed = seed; k.step = (int)t; k.p_in = ctx->cv.drop_in; k.p_fm = ctx->cv.drop_fm;
       cv_backward<<<(int)((GA + BQ - 1) / BQ), CT, back_smem, st>>>(k);
       KP_LAUNCHED(ctx, 2);
     }

@@ -169,4 +169,5 @@ int kp_conve_features(kp_ctx* ctx, int Q, const int32_t* triples, int stride, co
                       float* x_out, cudaStream_t st);
 int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32_t* rel_ids, int stride,
                          const float* mimic, const int32_t* mimic_index, float* x_out, float* feat_out,
-                         cudaStream_t st);
+                         cudaStream_t st, const int32_t* drop_ids = nullptr, unsigned long long seed = 0,
+                         int step = 0);

@@ -21,6 +21,7 @@ struct CxPlan {
   // per slot
   int32_t* a_cand; int32_t* a_rel; int32_t* a_truth;
   int32_t* b_cand; int32_t* b_lhs; int32_t* b_rel;
+  int32_t* b_row;  // nullable: global row / pair index of each B slot
 };
 
 // rows of candidate c used by global step t: returns B and the first row index
@@ -118,6 +119,7 @@ __global__ void cx_assign(const CxPlan p, int t) {
       p.b_cand[b] = c;
       p.b_lhs[b] = r[0];
       p.b_rel[b] = r[1];
+      if (p.b_row) p.b_row[b] = (int32_t)(first + i);
       ++b;
     }
   }

@@ -69,7 +69,14 @@ class PostTrainingEngine(RelevanceEngine):
         raise NotImplementedError
 
     # ---- batched core ---------------------------------------------------------------------
-    def individual_results(self, items):
+    @staticmethod
+    def _rng_snapshot():
+        state = [torch.get_rng_state(), np.random.get_state()]
+        if torch.cuda.is_available() and torch.cuda.is_initialized():
+            state.append(torch.cuda.get_rng_state())
+        return state
+
+    def individual_results(self, items, snapshots=None):
         """[(pred, rule)] -> [(pt_results, base_pt_results)], RNG drawn in sequential-call order.
 
         One mimic post-training job per candidate plus one per prediction whose homologous
@@ -97,6 +104,8 @@ class PostTrainingEngine(RelevanceEngine):
             job_filter.append(sorted(set(ds.to_filter.get((kp[0], kp[1]), []))))
             self._undo(ds)
             slots.append((pred, j))
+            if snapshots is not None:  # generator state after this candidate's draws (builder early stop)
+                snapshots.append(self._rng_snapshot())
 
         arrs = batch.arrays()
         hp = runtime.make_hp(kind, self.hp)
@@ -139,8 +148,10 @@ class NecessaryPostTrainingEngine(PostTrainingEngine):
     def compute_relevance(self, pred, triples):
         return self.compute_relevances(pred, [triples])[0]
 
-    def compute_relevances(self, pred, rules):
-        return [self._relevance(pt, base) for pt, base in self.individual_results([(pred, r) for r in rules])]
+    def compute_relevances(self, pred, rules, snapshots=False):
+        snaps = [] if snapshots else None
+        rels = [self._relevance(pt, base) for pt, base in self.individual_results([(pred, r) for r in rules], snaps)]
+        return (rels, snaps) if snapshots else rels
 
 
 class SufficientPostTrainingEngine(PostTrainingEngine):
@@ -164,13 +175,15 @@ class SufficientPostTrainingEngine(PostTrainingEngine):
     def compute_relevance(self, pred, rule):
         return self.compute_relevances(pred, [rule])[0]
 
-    def compute_relevances(self, pred, rules):
+    def compute_relevances(self, pred, rules, snapshots=False):
         """post_training_engine.py:178-191 for every rule: rule-major, conversion-entity-minor."""
         s = pred[0]
         items = []
         for rule in rules:
             for e in self.entities_to_convert:
                 items.append((Dataset.replace_entity_in_triple(pred, s, e), Dataset.replace_entity_in_triples(rule, s, e)))
-        res = [self._relevance(pt, base) for pt, base in self.individual_results(items)]
+        snaps = [] if snapshots else None
+        res = [self._relevance(pt, base) for pt, base in self.individual_results(items, snaps)]
         k = len(self.entities_to_convert)
-        return [sum(res[i * k:(i + 1) * k]) / k for i in range(len(rules))]
+        rels = [sum(res[i * k:(i + 1) * k]) / k for i in range(len(rules))]
+        return (rels, snaps[k - 1::k]) if snapshots else rels
