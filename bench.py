@@ -46,8 +46,8 @@ PRESETS = {
     "transe_yago4_20": dict(kind="TransE", N=96_000, dim=128, R=74, C=4096, T=(20, 60), init="xavier",
                             hp=dict(batch_size=2048, epochs=59, lr=0.01, margin=10, negative_triples_ratio=5,
                                     regularizer_weight=0.0)),
-    # configs[2] shape (configs/ConvE_DB100K_explanation.json); dropout forced to 0 (this build), stated
-    "conve_db100k": dict(kind="ConvE", N=99_604, dim=200, R=470, C=1024, T=(2, 20), init="xavier",
+    # configs[2] shape (configs/ConvE_DB100K_explanation.json), hidden dropout 0.2 as in the config
+    "conve_db100k": dict(kind="ConvE", N=99_604, dim=200, R=470, C=1024, T=(2, 20), init="xavier", dropout=(0.0, 0.0, 0.2),
                          hp=dict(batch_size=512, label_smoothing=0.1, lr=0.0432, decay=0.995, epochs=109)),
 }
 
@@ -78,7 +78,7 @@ def make_tables(cfg, device, seed=42):
         conve = dict(
             conv_w=torch.randn(32, 1, 3, 3, generator=cg) * 0.3, conv_b=torch.randn(32, generator=cg) * 0.1,
             fc_w=torch.randn(D, hidden, generator=cg) * (1.0 / hidden) ** 0.5, fc_b=torch.randn(D, generator=cg) * 0.1,
-            dropout=(0.0, 0.0, 0.0),
+            dropout=tuple(cfg.get("dropout", (0.0, 0.0, 0.0))),
         )
         for i, n in ((1, 1), (2, 32), (3, D)):
             conve[f"bn{i}_w"] = torch.rand(n, generator=cg) * 0.5 + 0.75
@@ -184,6 +184,7 @@ def run_reference(cfg, args, D, rank):
     kw = dict(norm=2, init_scale=1e-3)
     if kind == "ConvE":
         kw["conve"] = {k: v for k, v in conve.items() if k != "dropout"}
+        kw["dropout"] = conve["dropout"]
     w = ko.Weights(kind, ent, rel, **kw)
     kg = ko.KG(np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), N, R)
     n = args.warmup + args.steps
@@ -369,6 +370,7 @@ def cpu_baseline(cfg, D, ent, rel, conve):
     kw = dict(norm=2, init_scale=1e-3)
     if kind == "ConvE":
         kw["conve"] = {k: v.cpu() for k, v in conve.items() if k != "dropout"}
+        kw["dropout"] = conve["dropout"]
     w = ko.Weights(kind, ent.cpu(), rel.cpu(), **kw)
     kg = ko.KG(np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), N, R)
     budget, n, t_total = 20.0, 0, 0.0

@@ -28,6 +28,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->force_simt = value;
     return KP_OK;
   }
+  if (!strcmp(name, "force_tile")) {
+    ctx->force_tile = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "umma_cq")) {
     if (value != 0 && value != 1 && value != 2 && value != 4) KP_FAIL(ctx, KP_EINVAL, "umma_cq must be 0, 1, 2 or 4");
     ctx->umma_cq = value;

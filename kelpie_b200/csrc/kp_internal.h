@@ -53,6 +53,7 @@ struct kp_ctx {
 
   int64_t launches = 0;
   int64_t force_simt = 0;
+  int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_cq = 0;  // query tiles per cluster of the tcgen05 pass (0 = automatic)
 
   // optional per-category kernel timing (kp_set_option("timing", 1); read with kp_stat)
@@ -152,6 +153,9 @@ struct kp_pass_args {
   uint32_t* best;   // [Qn] order-preserving uint encoding of the best other score
 };
 int kp_pass_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st);
+// kp_stream.cu: same contract for Q <= 8 queries (HBM-streaming, no smem staging)
+bool kp_stream_usable(kp_ctx* ctx, int Qn);
+int kp_stream_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st);
 
 // ---- kp_score.cu : query preparation, rank finalisation ----------------------------------
 int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic, float* out,

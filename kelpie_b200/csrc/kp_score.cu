@@ -228,7 +228,7 @@ int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic
   if (!want_rank) {
     a.out = out;
     a.out_ld = out_ld;
-    if ((rc = kp_pass_launch(ctx, a, st)) != KP_OK) return rc;
+    if ((rc = (kp_stream_usable(ctx, Q) ? kp_stream_launch(ctx, a, st) : kp_pass_launch(ctx, a, st))) != KP_OK) return rc;
     if (mimic) {
       store_self<<<(Q + 255) / 256, 256, 0, st>>>(Q, N, self, out, out_ld);
       KP_LAUNCHED(ctx, 1);
@@ -248,7 +248,7 @@ int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic
   a.flt_ids = ids;
   a.cnt = cnt;
   a.best = best;
-  if ((rc = kp_pass_launch(ctx, a, st)) != KP_OK) return rc;
+  if ((rc = (kp_stream_usable(ctx, Q) ? kp_stream_launch(ctx, a, st) : kp_pass_launch(ctx, a, st))) != KP_OK) return rc;
   finalize_ranks<<<(Q + 255) / 256, 256, 0, st>>>(Q, N, mode, minimize ? 1 : 0, mimic ? 1 : 0, cnt, best, target, self,
                                                  tgt_ent, fbeg, fend, ids, target_score, best_score, rank, counters);
   KP_LAUNCHED(ctx, 1);

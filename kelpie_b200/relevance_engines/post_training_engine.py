@@ -109,7 +109,10 @@ class PostTrainingEngine(RelevanceEngine):
 
         arrs = batch.arrays()
         hp = runtime.make_hp(kind, self.hp)
-        rows = ctx.post_train(hp, **arrs)
+        # ConvE dropout masks are counter-based (kp_dropout.cuh); the seed advances per batch and
+        # does not touch the host generators (the reference draws its masks on the CUDA generator)
+        self._batches = getattr(self, "_batches", 0) + 1
+        rows = ctx.post_train(hp, dropout_seed=(42 << 32) | self._batches, **arrs)
         flt_off = np.zeros(len(job_filter) + 1, dtype=np.int64)
         flt_off[1:] = np.cumsum([len(f) for f in job_filter])
         flt_ids = np.array([x for f in job_filter for x in f], dtype=np.int32)

@@ -149,3 +149,32 @@ def test_post_training_is_deterministic_and_batch_order_independent():
     b = run([jobs[i] for i in perm])
     scale = np.abs(a).max(axis=1, keepdims=True)
     assert (np.abs(b - a[perm]) / scale[perm]).max() < 1e-5  # a candidate does not depend on its neighbours
+
+
+@pytest.mark.parametrize("kind", ["TransE", "ComplEx", "ConvE"])
+@pytest.mark.parametrize("Q", [1, 3, 8])
+def test_streaming_pass_equals_tile_pass(kind, Q):
+    """Few-query HBM-streaming kernel (kp_stream.cu) vs the 64-query tile kernel (kp_pass.cu)."""
+    from kelpie_b200 import runtime
+    z, meta, kg, w, order = load(kind)
+    ctx = _ctx(kind, z, w)
+    N = kg.num_entities
+    rng = np.random.default_rng(Q)
+    triples = np.stack([rng.integers(0, N, Q), rng.integers(0, 2 * kg.num_relations, Q), rng.integers(0, N, Q)], 1)
+    mimic = (rng.standard_normal((Q, w.dim)) * 0.1).astype(np.float32)
+    triples[0, 0] = N  # one query whose lhs is its mimic row
+    lens = rng.integers(0, 30, Q)
+    off = np.zeros(Q + 1, dtype=np.int64)
+    off[1:] = np.cumsum(lens)
+    ids = np.concatenate([np.sort(rng.choice(N + 1, n, replace=False)) for n in lens] + [np.zeros(0, np.int64)]).astype(np.int32)
+    res = {}
+    for tile in (0, 1):
+        ctx.set_option("force_tile", tile)
+        sc = ctx.all_scores(triples, mimic_rows=mimic).cpu().numpy()
+        out = [t.cpu().numpy() for t in ctx.filtered_rank(triples, runtime.RANK_ENGINE_MIN if kind == "TransE" else runtime.RANK_ENGINE_MAX,
+                                                            mimic_rows=mimic, flt_off=off, flt_ids=ids if len(ids) else None, counters=True)]
+        res[tile] = (sc, out)
+    np.testing.assert_allclose(res[0][0], res[1][0], rtol=2e-5, atol=1e-6)
+    np.testing.assert_array_equal(res[0][1][2], res[1][1][2])   # ranks
+    np.testing.assert_array_equal(res[0][1][3], res[1][1][3])   # counters
+    np.testing.assert_allclose(res[0][1][0], res[1][1][0], rtol=2e-5, atol=1e-6)
