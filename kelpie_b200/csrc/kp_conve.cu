@@ -9,7 +9,6 @@
 namespace {
 
 constexpr int CV_THREADS = 256;
-constexpr int CV_QB = 4;  // queries per CTA (share every fc_w row read)
 
 struct ConvK {
   int Q, N, R2, D, H, F, hidden, stride;
@@ -36,39 +35,29 @@ __device__ __forceinline__ void bn_affine(const float* bn, int n, int i, float& 
   beta = bn[n + i] - bn[2 * n + i] * alpha;
 }
 
-__global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK p) {
+// Stage 1 (one CTA per pair): stacked image -> BN1 (+input dropout) -> Conv 3x3 -> BN2 -> ReLU
+// (+Dropout2d) -> feat[q, hidden]
+__global__ void __launch_bounds__(CV_THREADS) conve_conv_kernel(const ConvK p) {
   extern __shared__ float sm[];
   const int H = p.H, W2 = H - 2, D = p.D;
   const int img_sz = 40 * H;
-  float* img = sm;                          // [QB][40*H]
-  float* feat = img + CV_QB * img_sz;       // [QB][hidden]
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int qbase = blockIdx.x * CV_QB;
-
+  float* img = sm;  // [40*H]
+  const int tid = threadIdx.x, q = blockIdx.x;
   float a1, b1;
   bn_affine(p.bn1, 1, 0, a1, b1);
-  for (int i = tid; i < CV_QB * img_sz; i += CV_THREADS) {
-    const int qb = i / img_sz, k = i % img_sz, q = qbase + qb;
-    float v = 0.f;
-    if (q < p.Q) {
-      const int s = p.lhs_ids ? p.lhs_ids[(size_t)q * p.stride] : p.N, r = p.rel_ids[(size_t)q * p.stride];
-      if (k < D) {
-        const float* l = (s == p.N) ? p.mimic + (size_t)(p.mimic_index ? p.mimic_index[q] : q) * D : p.ent + (size_t)s * D;
-        v = l[k];
-      } else {
-        v = p.rel[(size_t)r * D + (k - D)];
-      }
-      v = v * a1 + b1;
-      if (p.drop_ids && p.p_in > 0.f) v *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_INPUT + k, p.p_in);
-    }
-    img[i] = v;
+  const int s = p.lhs_ids ? p.lhs_ids[(size_t)q * p.stride] : p.N, r = p.rel_ids[(size_t)q * p.stride];
+  const float* l = (s == p.N) ? p.mimic + (size_t)(p.mimic_index ? p.mimic_index[q] : q) * D : p.ent + (size_t)s * D;
+  for (int k = tid; k < img_sz; k += CV_THREADS) {
+    float v = (k < D) ? l[k] : p.rel[(size_t)r * D + (k - D)];
+    v = v * a1 + b1;
+    if (p.drop_ids && p.p_in > 0.f) v *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_INPUT + k, p.p_in);
+    img[k] = v;
   }
   __syncthreads();
   const int per_f = 38 * W2;
-  for (int i = tid; i < CV_QB * p.hidden; i += CV_THREADS) {
-    const int qb = i / p.hidden, o = i % p.hidden;
+  for (int o = tid; o < p.hidden; o += CV_THREADS) {
     const int c = o / per_f, y = (o % per_f) / W2, x = o % W2;
-    const float* im = img + qb * img_sz + y * H + x;
+    const float* im = img + y * H + x;
     const float* w = p.conv_w + c * 9;
     float acc = p.conv_b[c];
 #pragma unroll
@@ -78,44 +67,21 @@ __global__ void __launch_bounds__(CV_THREADS) conve_features_kernel(const ConvK 
     float a2, b2;
     bn_affine(p.bn2, p.F, c, a2, b2);
     acc = fmaxf(acc * a2 + b2, 0.f);
-    if (p.drop_ids && p.p_fm > 0.f && qbase + qb < p.Q)  // Dropout2d: whole channels
-      acc *= kp_drop_scale(p.seed, p.drop_ids[qbase + qb], p.step, KP_DROP_FEATURE + c, p.p_fm);
-    feat[i] = acc;
-    if (p.feat_out && qbase + qb < p.Q) p.feat_out[(size_t)(qbase + qb) * p.hidden + o] = acc;
+    if (p.drop_ids && p.p_fm > 0.f) acc *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_FEATURE + c, p.p_fm);
+    p.feat_out[(size_t)q * p.hidden + o] = acc;
   }
-  __syncthreads();
-  for (int k = warp; k < D; k += CV_THREADS / 32) {
-    const float* w = p.fc_w + (size_t)k * p.hidden;
-    float acc[CV_QB];
-#pragma unroll
-    for (int qb = 0; qb < CV_QB; ++qb) acc[qb] = 0.f;
-    for (int i = lane * 4; i < p.hidden; i += 128) {
-      const float4 wv = *reinterpret_cast<const float4*>(w + i);
-#pragma unroll
-      for (int qb = 0; qb < CV_QB; ++qb) {
-        const float4 f = *reinterpret_cast<const float4*>(feat + qb * p.hidden + i);
-        acc[qb] += wv.x * f.x + wv.y * f.y + wv.z * f.z + wv.w * f.w;
-      }
-    }
-#pragma unroll
-    for (int qb = 0; qb < CV_QB; ++qb) {
-      float v = acc[qb];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      acc[qb] = v;
-    }
-    if (lane == 0) {
-      float a3, b3;
-      bn_affine(p.bn3, D, k, a3, b3);
-#pragma unroll
-      for (int qb = 0; qb < CV_QB; ++qb)
-        if (qbase + qb < p.Q) {
-          float h = acc[qb] + p.fc_b[k];
-          if (p.drop_ids && p.p_hid > 0.f) h *= kp_drop_scale(p.seed, p.drop_ids[qbase + qb], p.step, KP_DROP_HIDDEN + k, p.p_hid);
-          p.x_out[(size_t)(qbase + qb) * D + k] = fmaxf(h * a3 + b3, 0.f);
-        }
-    }
-  }
+}
+
+// Stage 3: x = ReLU(BN3(dropout(raw + fc_b)))   (stage 2 is the Linear GEMM, kp_gemm.cu)
+__global__ void conve_head_kernel(const ConvK p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (size_t)p.Q * p.D) return;
+  const int q = (int)(i / p.D), k = (int)(i % p.D);
+  float a3, b3;
+  bn_affine(p.bn3, p.D, k, a3, b3);
+  float h = p.x_out[i] + p.fc_b[k];
+  if (p.drop_ids && p.p_hid > 0.f) h *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_HIDDEN + k, p.p_hid);
+  p.x_out[i] = fmaxf(h * a3 + b3, 0.f);
 }
 
 __global__ void colsum_kernel(int N, int D, const float* __restrict__ ent, float* __restrict__ out) {
@@ -211,16 +177,35 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
   p.bn3 = ctx->cv.bn3;
   p.x_out = x_out;
   p.feat_out = feat_out;
-  const size_t smem = (size_t)CV_QB * (40 * p.H + p.hidden) * sizeof(float);
-  static bool configured = false;
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(conve_features_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
+  // feature maps go to the caller's buffer (kept for the backward pass) or to scratch, in chunks
+  const int chunk = feat_out ? Q : (Q < 4096 ? Q : 4096);
+  float* scratch = feat_out;
+  if (!feat_out) {
+    int rc = kp_ws_reserve(ctx, (size_t)chunk * p.hidden * sizeof(float) + 1024, 1);
+    if (rc != KP_OK) return rc;
+    scratch = reinterpret_cast<float*>(ctx->ws_arena[1]);
   }
-  if (smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", p.hidden);
-  KpTimer timer(ctx, kp_ctx::T_CONV, st);
-  conve_features_kernel<<<(Q + CV_QB - 1) / CV_QB, CV_THREADS, smem, st>>>(p);
-  KP_LAUNCHED(ctx, 1);
+  for (int q0 = 0; q0 < Q; q0 += chunk) {
+    const int n = (Q - q0 < chunk) ? Q - q0 : chunk;
+    ConvK c = p;
+    c.Q = n;
+    c.lhs_ids = lhs_ids ? lhs_ids + (size_t)q0 * stride : nullptr;
+    c.rel_ids = rel_ids + (size_t)q0 * stride;
+    c.mimic = (mimic && !mimic_index) ? mimic + (size_t)q0 * p.D : mimic;
+    c.mimic_index = mimic_index ? mimic_index + q0 : nullptr;
+    c.drop_ids = drop_ids ? drop_ids + q0 : nullptr;
+    c.x_out = x_out + (size_t)q0 * p.D;
+    c.feat_out = feat_out ? feat_out + (size_t)q0 * p.hidden : scratch;
+    {
+      KpTimer timer(ctx, kp_ctx::T_CONV, st);
+      conve_conv_kernel<<<n, CV_THREADS, (size_t)40 * p.H * sizeof(float), st>>>(c);
+    }
+    KP_LAUNCHED(ctx, 1);
+    int rc = kp_sgemm(ctx, true, n, p.D, p.hidden, c.feat_out, p.hidden, p.fc_w, p.hidden, c.x_out, p.D, st);
+    if (rc != KP_OK) return rc;
+    conve_head_kernel<<<(int)(((size_t)n * p.D + 255) / 256), 256, 0, st>>>(c);
+    KP_LAUNCHED(ctx, 1);
+  }
   return KP_OK;
 }
 

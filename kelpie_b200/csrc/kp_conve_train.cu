@@ -23,7 +23,6 @@
 namespace {
 
 constexpr int CT = 256;
-constexpr int BQ = 4;  // slots per CTA in the backward kernel (share every fc_w read)
 
 __device__ __forceinline__ float blk_sum(float v, float* red) {
   __syncthreads();
@@ -93,54 +92,35 @@ __global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
 
 struct CvBack {
   int GA, D, H, F, hidden;
-  const float *fc_w, *conv_w, *bn1, *bn2;
-  const float* feat;  // [GA, hidden] post-ReLU (and post-dropout) feature maps saved by the forward kernel
-  const float* dh;    // [GA, D]
-  float* glhs;        // [GA, D] gradient w.r.t. the lhs embedding
-  const int32_t* pair;  // [GA] pair ids keying the dropout masks
+  const float *conv_w, *bn1, *bn2;
+  const float* feat;   // [GA, hidden] post-ReLU (and post-dropout) feature maps saved by the forward kernel
+  const float* dfeat;  // [GA, hidden] = dh @ fc_w  (Linear^T, kp_gemm.cu)
+  float* glhs;         // [GA, D] gradient w.r.t. the lhs embedding
+  const int32_t* pair; // [GA] pair ids keying the dropout masks
   unsigned long long seed;
   int step;
   float p_in, p_fm;
 };
 
+// One CTA per pair: ReLU / BN2 (/Dropout2d) backward, Conv^T restricted to the lhs half of the
+// 40 x H image, BN1 (/input dropout) backward.
 __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
   extern __shared__ float bsm[];
   const int D = p.D, H = p.H, W2 = H - 2, hidden = p.hidden, per_f = 38 * W2;
-  float* dh = bsm;              // [BQ][D]
-  float* dcv = dh + BQ * D;     // [BQ][hidden]
-  const int tid = threadIdx.x, g0 = blockIdx.x * BQ;
-  for (int i = tid; i < BQ * D; i += CT) {
-    const int qb = i / D, k = i % D;
-    dh[i] = (g0 + qb < p.GA) ? p.dh[(size_t)(g0 + qb) * D + k] : 0.f;
-  }
-  __syncthreads();
-  // Linear^T, then ReLU / BN2 backward
+  float* dcv = bsm;  // [hidden]
+  const int tid = threadIdx.x, g = blockIdx.x;
   for (int i = tid; i < hidden; i += CT) {
-    float acc[BQ];
-#pragma unroll
-    for (int qb = 0; qb < BQ; ++qb) acc[qb] = 0.f;
-    for (int k = 0; k < D; ++k) {
-      const float w = p.fc_w[(size_t)k * hidden + i];
-#pragma unroll
-      for (int qb = 0; qb < BQ; ++qb) acc[qb] = __fmaf_rn(w, dh[qb * D + k], acc[qb]);
-    }
     const int c = i / per_f;
     const float a2 = p.bn2[c] / sqrtf(p.bn2[3 * p.F + c] + 1e-5f);
-#pragma unroll
-    for (int qb = 0; qb < BQ; ++qb) {
-      const bool on = (g0 + qb < p.GA) && p.feat[(size_t)(g0 + qb) * hidden + i] > 0.f;  // dropped channels are 0
-      float d = on ? acc[qb] * a2 : 0.f;
-      if (on && p.p_fm > 0.f) d *= kp_drop_scale(p.seed, p.pair[g0 + qb], p.step, KP_DROP_FEATURE + c, p.p_fm);
-      dcv[qb * hidden + i] = d;
-    }
+    const bool on = p.feat[(size_t)g * hidden + i] > 0.f;  // dropped channels are 0
+    float d = on ? p.dfeat[(size_t)g * hidden + i] * a2 : 0.f;
+    if (on && p.p_fm > 0.f) d *= kp_drop_scale(p.seed, p.pair[g], p.step, KP_DROP_FEATURE + c, p.p_fm);
+    dcv[i] = d;
   }
   __syncthreads();
-  // Conv^T restricted to the lhs half of the 40 x H image, then BN1 backward
   const float a1 = p.bn1[0] / sqrtf(p.bn1[3] + 1e-5f);
-  for (int i = tid; i < BQ * D; i += CT) {
-    const int qb = i / D, k = i % D, y = k / H, x = k % H;
-    if (g0 + qb >= p.GA) continue;
-    const float* dc = dcv + qb * hidden;
+  for (int k = tid; k < D; k += CT) {
+    const int y = k / H, x = k % H;
     float acc = 0.f;
     for (int c = 0; c < p.F; ++c) {
       const float* w = p.conv_w + c * 9;
@@ -152,12 +132,12 @@ __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
         for (int dx = 0; dx < 3; ++dx) {
           const int xx = x - dx;
           if (xx < 0 || xx >= W2) continue;
-          acc = __fmaf_rn(w[dy * 3 + dx], dc[c * per_f + yy * W2 + xx], acc);
+          acc = __fmaf_rn(w[dy * 3 + dx], dcv[c * per_f + yy * W2 + xx], acc);
         }
       }
     }
-    if (p.p_in > 0.f) acc *= kp_drop_scale(p.seed, p.pair[g0 + qb], p.step, KP_DROP_INPUT + k, p.p_in);
-    p.glhs[(size_t)(g0 + qb) * D + k] = acc * a1;
+    if (p.p_in > 0.f) acc *= kp_drop_scale(p.seed, p.pair[g], p.step, KP_DROP_INPUT + k, p.p_in);
+    p.glhs[(size_t)g * D + k] = acc * a1;
   }
 }
 
@@ -232,7 +212,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
 
   size_t need = 3 * WsCursor::need((size_t)C * D, 4) + 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8) +
                 7 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
-                WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
+                2 * WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
                 2 * WsCursor::need((size_t)S * G, 4) + WsCursor::need((size_t)S * G * D, 4);
   int rc = kp_ws_reserve(ctx, need);
   if (rc != KP_OK) return rc;
@@ -250,6 +230,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   float* xA = ws.take<float>((size_t)Gpad * D);
   float* xB = ws.take<float>((size_t)Gpad * D);
   float* feat = ws.take<float>((size_t)G * hidden);
+  float* dfeat = ws.take<float>((size_t)G * hidden);
   float* dh = ws.take<float>((size_t)G * D);
   float* glhs = ws.take<float>((size_t)G * D);
   float* colcoef = ws.take<float>(G);
@@ -267,7 +248,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   const int cb = (C + 127) / 128;
   int64_t GA = 0, GB = 0;
   static bool configured = false;
-  const size_t back_smem = (size_t)BQ * (D + hidden) * sizeof(float);
+  const size_t back_smem = (size_t)hidden * sizeof(float);
   if (back_smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", hidden);
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -309,11 +290,13 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
       cv_dx<<<(int)GA, CT, (size_t)D * 4, st>>>(d);
       CvBack k;
       k.GA = (int)GA; k.D = D; k.H = ctx->cv.H; k.F = ctx->cv.n_filters; k.hidden = hidden;
-      k.fc_w = ctx->cv.fc_w; k.conv_w = ctx->cv.conv_w; k.bn1 = ctx->cv.bn1; k.bn2 = ctx->cv.bn2;
-      k.feat = feat; k.dh = dh; k.glhs = glhs;
+      k.conv_w = ctx->cv.conv_w; k.bn1 = ctx->cv.bn1; k.bn2 = ctx->cv.bn2;
+      k.feat = feat; k.dfeat = dfeat; k.glhs = glhs;
       k.pair = pl.a_truth; k.seed = seed; k.step = (int)t; k.p_in = ctx->cv.drop_in; k.p_fm = ctx->cv.drop_fm;
-      cv_backward<<<(int)((GA + BQ - 1) / BQ), CT, back_smem, st>>>(k);
-      KP_LAUNCHED(ctx, 2);
+      KP_LAUNCHED(ctx, 1);
+      if ((rc = kp_sgemm(ctx, false, (int)GA, hidden, D, dh, D, ctx->cv.fc_w, hidden, dfeat, hidden, st)) != KP_OK) return rc;
+      cv_backward<<<(int)GA, CT, back_smem, st>>>(k);
+      KP_LAUNCHED(ctx, 1);
     }
     if (GA + GB > 0) {
       CvUpd u;

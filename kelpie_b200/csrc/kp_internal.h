@@ -175,3 +175,5 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
                          const float* mimic, const int32_t* mimic_index, float* x_out, float* feat_out,
                          cudaStream_t st, const int32_t* drop_ids = nullptr, unsigned long long seed = 0,
                          int step = 0);
+int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
+             int ldc, cudaStream_t st);
