@@ -43,26 +43,49 @@ __global__ void prep_queries(int kind, int Q, int N, int R2, int D, const float*
   }
 }
 
-__device__ __forceinline__ float pair_score(int op, int act, const float* a, const float* b, int D, int lane) {
-  float acc = 0.f;
-  for (int k = lane; k < D; k += 32) {
-    const float x = a[k], y = b[k];
-    if (op == KP_OP_DOT)
-      acc = __fmaf_rn(x, y, acc);
-    else if (op == KP_OP_L2) {
-      const float d = __fsub_rn(x, y);
-      acc = __fmaf_rn(d, d, acc);
-    } else
-      acc += fabsf(__fsub_rn(x, y));
+// Score of one (query, row) pair with EXACTLY the arithmetic of the pass kernel that will scan the
+// table, so that the target's score equals the score that kernel computes for row o (entities
+// with identical embeddings then tie exactly, as they do in the reference's single matmul):
+//   tile kernel (kp_pass.cu)   : one sequential fp32 FMA chain over k = 0 .. D-1
+//   stream kernel (kp_stream.cu): lane l accumulates the float4 at (v*32 + l)*4, v = 0,1,..; then a
+//                                 butterfly over lane offsets 16, 8, 4, 2, 1
+__device__ __forceinline__ float term(int op, float acc, float x, float y) {
+  if (op == KP_OP_DOT) return __fmaf_rn(x, y, acc);
+  if (op == KP_OP_L2) {
+    const float d = __fsub_rn(x, y);
+    return __fmaf_rn(d, d, acc);
   }
-  acc = warp_sum(acc);
+  return __fadd_rn(acc, fabsf(__fsub_rn(x, y)));
+}
+
+__device__ __forceinline__ float pair_score(int op, int act, bool stream, const float* a, const float* b, int D, int lane) {
+  float acc = 0.f;
+  if (!stream) {
+    if (lane == 0)
+      for (int k = 0; k < D; ++k) acc = term(op, acc, a[k], b[k]);
+    acc = __shfl_sync(0xffffffffu, acc, 0);
+  } else {
+    for (int k = lane * 4; k < D; k += 128) {
+      if (op == KP_OP_L1) {  // the stream kernel adds the four |d| of a float4 before accumulating
+        acc += fabsf(a[k] - b[k]) + fabsf(a[k + 1] - b[k + 1]) + fabsf(a[k + 2] - b[k + 2]) + fabsf(a[k + 3] - b[k + 3]);
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (op == KP_OP_DOT) acc = __fmaf_rn(a[k + c], b[k + c], acc);
+          else { const float d = a[k + c] - b[k + c]; acc = __fmaf_rn(d, d, acc); }
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  }
   if (op == KP_OP_L2) acc = sqrtf(acc);
   if (act == KP_ACT_SIGMOID) acc = 1.f / (1.f + expf(-acc));
   return acc;
 }
 
 // One warp per query: score of the target o_q and of the query's own mimic row (column N).
-__global__ void target_scores(int op, int act, int Q, int N, int D, const float* __restrict__ ent,
+__global__ void target_scores(int op, int act, int stream, int Q, int N, int D, const float* __restrict__ ent,
                               const int32_t* __restrict__ triples, const float* __restrict__ mimic,
                               const float* __restrict__ qmat, float* __restrict__ target,
                               float* __restrict__ self, int32_t* __restrict__ tgt_ent) {
@@ -74,9 +97,9 @@ __global__ void target_scores(int op, int act, int Q, int N, int D, const float*
   float t = __int_as_float(0x7fc00000), sf = 0.f;
   if (o >= 0 && (o < N || (o == N && mimic))) {
     const float* b = (o == N) ? mimic + (size_t)q * D : ent + (size_t)o * D;
-    t = pair_score(op, act, a, b, D, lane);
+    t = pair_score(op, act, stream != 0, a, b, D, lane);
   }
-  if (mimic) sf = pair_score(op, act, a, mimic + (size_t)q * D, D, lane);
+  if (mimic) sf = pair_score(op, act, stream != 0, a, mimic + (size_t)q * D, D, lane);
   if (lane == 0) {
     target[q] = t;
     self[q] = sf;
@@ -222,7 +245,7 @@ int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic
   a.act = act;
   a.minimize = minimize;
   if (want_rank || mimic) {
-    target_scores<<<nb, wpb * 32, 0, st>>>(op, act, Q, N, D, ctx->ent, triples, mimic, qmat, target, self, tgt_ent);
+    target_scores<<<nb, wpb * 32, 0, st>>>(op, act, kp_stream_usable(ctx, Q) ? 1 : 0, Q, N, D, ctx->ent, triples, mimic, qmat, target, self, tgt_ent);
     KP_LAUNCHED(ctx, 1);
   }
   if (!want_rank) {
