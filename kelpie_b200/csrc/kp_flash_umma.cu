@@ -367,19 +367,23 @@ struct UPlan {
   int Dpad;    // padded row width of the split tables
   int n_qt;    // query tiles, padded to a multiple of cq
   int n_strips, n_tiles, tps;
+  bool pair;   // cta_group::2 kernel (kp_flash_umma2.cu): SM pairs over 2 query tiles
 };
 UPlan umma_plan(kp_ctx* ctx, int G) {
   UPlan u;
   u.KBs = (ctx->D + 63) / 64;
   u.cc = u.KBs <= 4 ? 1 : 2;  // dim chunks (clustered together only when cq > 1)
   u.bpc = (u.KBs + u.cc - 1) / u.cc;
+  u.bpc = (u.bpc + 1) & ~1;  // whole 128-dim groups (the cta_group::2 pass contracts two boxes per MMA)
   u.Dpad = (u.KBs > u.bpc * u.cc ? u.KBs : u.bpc * u.cc) * 64;
   const int n_qt = (G + 127) / 128;
+  u.pair = ctx->umma_2sm != 0 && ctx->umma_cq <= 1 && n_qt >= 2;
   // default: independent CTAs.  Measured on B200 (1M x 512, 18k rows): clusters of 2x2 with TMA
   // multicast run at 159 TFLOP/s vs 219 without -- the per-SM shared-memory fill rate, which
   // multicast does not lower, is the limiter, and the lock-step slot release costs more than it saves.
   int cq = ctx->umma_cq > 0 ? (int)ctx->umma_cq : 1;
   while (cq > 1 && n_qt < cq) cq >>= 1;
+  if (u.pair) cq = 2;
   u.cq = cq;
   u.n_qt = ((n_qt + cq - 1) / cq) * cq;
   u.n_tiles = (int)((ctx->N + 127) / 128);
@@ -416,6 +420,8 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
     KP_LAUNCHED(ctx, 1);
     if ((rc = encode_bf16(ctx, &ctx->um.eh_map, h, Npad, Dpad)) != KP_OK) return rc;
     if ((rc = encode_bf16(ctx, &ctx->um.el_map, l, Npad, Dpad)) != KP_OK) return rc;
+    if ((rc = kp_encode_2d(ctx, &ctx->um.eh64_map, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
+    if ((rc = kp_encode_2d(ctx, &ctx->um.el64_map, l, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
     ctx->um.ent_hi = h;
     ctx->um.ent_lo = l;
     ctx->um.ready = true;
@@ -431,6 +437,9 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   if ((rc = encode_bf16(ctx, &qh_map, qh, Gpad, Dpad)) != KP_OK) return rc;
   if ((rc = encode_bf16(ctx, &ql_map, ql, Gpad, Dpad)) != KP_OK) return rc;
 
+  if (u.pair)
+    return kp_flash_umma2_launch(ctx, qh_map, ql_map, G, u.KBs, u.bpc / 2, u.cc, u.n_qt, u.n_strips, u.tps, mode, part_m,
+                                 part_l, part_O, st);
   UK p;
   p.G = G;
   p.N = (int)ctx->N;

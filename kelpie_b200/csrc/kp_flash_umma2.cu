@@ -1,0 +1,345 @@
+// cta_group::2 version of the fused score -> softmax/sigmoid -> contract pass (see
+// kp_flash_umma.cu for the algorithm, the bf16x3 split and the TMEM layout).
+//
+// Two CTAs on an SM pair (cluster 2x1x1) own two neighbouring query tiles and walk the same entity
+// tiles and dim chunk.  Every tcgen05.mma is issued by the even CTA with M = 256 (128 query rows
+// in each CTA's TMEM); the B operand of an MMA is split across the pair, so each SM stages only
+// HALF of every entity box:
+//   S  = Q E^T : N = 128 entities, each CTA loads 64 entity rows of the k-block (16 KB instead of 32)
+//   O += P E   : N = 128 dims,     each CTA loads one of the two 64-dim boxes     (2 boxes per tile instead of 4)
+// i.e. 448 KB of shared-memory fill per 128x128 tile and CTA instead of 640 KB -- the measured
+// limiter of the 1-SM kernel.  TMA loads of both CTAs complete on the even CTA's `full` barriers
+// (.cta_group::2 form); tcgen05.commit multicasts slot releases / S-ready / PV-done to both CTAs;
+// the odd CTA's softmax threads arrive remotely on the even CTA's P-ready barrier.
+#include <cuda_bf16.h>
+
+#include "kp_flash.cuh"
+#include "kp_internal.h"
+#include "kp_ptx.cuh"
+
+namespace {
+
+constexpr int UT = 192;
+constexpr int SLOT = 32768;
+constexpr int NSLOT = 6;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float RESCALE_TAU = 8.0f;
+
+struct UCtl2 {
+  uint64_t full[NSLOT], empty[NSLOT];
+  uint64_t s_full[2];
+  uint64_t p_full, pv_done, o_done;
+  uint32_t tmem_base;
+};
+constexpr size_t U2_SMEM = (size_t)NSLOT * SLOT + sizeof(UCtl2) + 1024;
+
+struct UK2 {
+  int G, N, D, KB, n_tiles, tiles_per_strip, groups_per_chunk, mode;
+  float* part_m;
+  float* part_l;
+  float* part_O;
+};
+
+__device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1)
+flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_constant__ CUtensorMap el_map,
+                   const __grid_constant__ CUtensorMap eh64_map, const __grid_constant__ CUtensorMap el64_map,
+                   const __grid_constant__ CUtensorMap qh_map, const __grid_constant__ CUtensorMap ql_map, const UK2 p) {
+  extern __shared__ uint8_t uraw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(uraw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = sm;
+  UCtl2* ctl = reinterpret_cast<UCtl2*>(sm + (size_t)NSLOT * SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int strip = blockIdx.y, qtile = blockIdx.x, chunk = blockIdx.z;  // the SM pair spans x
+  const int t0 = strip * p.tiles_per_strip;
+  const int t1 = min(t0 + p.tiles_per_strip, p.n_tiles);
+  const int ntile = t1 - t0;
+  if (ntile <= 0) return;  // uniform over the pair
+  const uint32_t crank = ptx::cluster_ctarank();  // 0 = leader (issues every MMA)
+  const bool leader = crank == 0;
+  const int ngroup = p.groups_per_chunk;           // 128-dim groups of this chunk (<= 2)
+  const int box0 = chunk * ngroup * 2;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) ptx::mbar_init(&ctl->s_full[b], 1);
+    ptx::mbar_init(&ctl->p_full, 256);  // 128 softmax threads of each CTA (used in the leader only)
+    ptx::mbar_init(&ctl->pv_done, 1);
+    ptx::mbar_init(&ctl->o_done, 1);
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(&ctl->tmem_base, 512);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tm = ctl->tmem_base;
+  const uint32_t TM_O = tm, TM_S = tm + 256;
+
+  if (warp == 0) {
+    // ------------------------------- TMA producer (both CTAs) -------------------------------
+    if (lane == 0) {
+      ptx::prefetch_tmap(&eh_map);
+      ptx::prefetch_tmap(&el_map);
+      ptx::prefetch_tmap(&eh64_map);
+      ptx::prefetch_tmap(&el64_map);
+      ptx::prefetch_tmap(&qh_map);
+      ptx::prefetch_tmap(&ql_map);
+      uint32_t use = 0;
+      // bytes_pair = bytes the two CTAs together deliver for this slot use (armed on the leader's barrier)
+      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row, uint32_t lo_off, uint32_t bytes_pair) {
+        const int s = use % NSLOT;
+        ptx::mbar_wait(&ctl->empty[s], ((use / NSLOT) & 1) ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], bytes_pair);
+        const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&ctl->full[s]), 0);
+        uint8_t* dst = ring + (size_t)s * SLOT;
+        ptx::tma_load_2d_pair(dst, hi, bar, col, row);
+        ptx::tma_load_2d_pair(dst + lo_off, lo, bar, col, row);
+        ++use;
+      };
+      for (int i = 0; i <= ntile; ++i) {
+        if (i < ntile)
+          for (int kb = 0; kb < p.KB; ++kb) {
+            load(&qh_map, &ql_map, kb * 64, qtile * 128, 16384, 2 * 32768);                         // my query tile
+            load(&eh64_map, &el64_map, kb * 64, (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the entities
+          }
+        if (i > 0)
+          for (int g = 0; g < ngroup; ++g)
+            load(&eh_map, &el_map, (box0 + 2 * g + (int)crank) * 64, (t0 + i - 1) * 128, 16384, 2 * 32768);  // my 64 dims
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------- MMA issuer (leader CTA only) -------------------------------
+    if (lane == 0 && leader) {
+      const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t ring_a = ptx::smem_u32(ring);
+      uint32_t use = 0;
+      auto wait_slot = [&](uint32_t u) { ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1); };
+      auto release = [&](uint32_t u) { ptx::umma2_commit_mc(&ctl->empty[u % NSLOT], 3); };
+      auto pv = [&](int t) {
+        ptx::mbar_wait_cluster(&ctl->p_full, t & 1);
+        ptx::tc_fence_after();
+        for (int g = 0; g < ngroup; ++g) {
+          wait_slot(use);
+          ptx::tc_fence_after();
+          const uint32_t e_hi = ring_a + (use % NSLOT) * SLOT, e_lo = e_hi + 16384;
+          const uint32_t d_o = TM_O + g * 128;
+          const uint32_t p_t = TM_S + (t & 1) * 128;
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t a_hi = p_t + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
+            const uint64_t b_hi = udesc(e_hi + ks * 2048, 16384, 1024), b_lo = udesc(e_lo + ks * 2048, 16384, 1024);
+            ptx::umma2_bf16_ts(d_o, a_hi, b_hi, idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
+            ptx::umma2_bf16_ts(d_o, a_hi, b_lo, idesc_pv, 1u);
+            ptx::umma2_bf16_ts(d_o, a_lo, b_hi, idesc_pv, 1u);
+          }
+          release(use);
+          ++use;
+        }
+        ptx::umma2_commit_mc(&ctl->pv_done, 3);
+      };
+      for (int i = 0; i < ntile; ++i) {
+        const int sb = i & 1;
+        const uint32_t d_s = TM_S + sb * 128;
+        for (int kb = 0; kb < p.KB; ++kb) {
+          wait_slot(use);
+          wait_slot(use + 1);
+          ptx::tc_fence_after();
+          const uint32_t q_hi = ring_a + (use % NSLOT) * SLOT, q_lo = q_hi + 16384;
+          const uint32_t e_hi = ring_a + ((use + 1) % NSLOT) * SLOT, e_lo = e_hi + 8192;
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint64_t a_hi = udesc(q_hi + kk * 32, 16, 1024), a_lo = udesc(q_lo + kk * 32, 16, 1024);
+            const uint64_t b_hi = udesc(e_hi + kk * 32, 16, 1024), b_lo = udesc(e_lo + kk * 32, 16, 1024);
+            ptx::umma2_bf16(d_s, a_hi, b_hi, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
+            ptx::umma2_bf16(d_s, a_hi, b_lo, idesc_s, 1u);
+            ptx::umma2_bf16(d_s, a_lo, b_hi, idesc_s, 1u);
+          }
+          release(use);
+          release(use + 1);
+          use += 2;
+        }
+        ptx::umma2_commit_mc(&ctl->s_full[sb], 3);
+        if (i > 0) pv(i - 1);
+      }
+      pv(ntile - 1);
+      ptx::umma2_commit_mc(&ctl->o_done, 3);
+    }
+  } else {
+    // ------------------------------- softmax / epilogue (both CTAs, own rows) -------------------------------
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
+    const int g = qtile * 128 + row;
+    const uint32_t p_full_leader = ptx::mapa_u32(ptx::smem_u32(&ctl->p_full), 0);
+    float m_ref = -INFINITY, l_run = 0.f;
+    const int ocols = ngroup * 128;
+    for (int i = 0; i < ntile; ++i) {
+      const int sb = i & 1;
+      const int j0 = (t0 + i) * 128;
+      ptx::mbar_wait(&ctl->s_full[sb], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t s_addr = TM_S + sb * 128 + lane_off;
+      float factor = 1.f;
+      if (p.mode == KP_FLASH_SOFTMAX) {
+        float mx = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(s_addr + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (j0 + c0 + c < p.N) mx = fmaxf(mx, __uint_as_float(r[c]));
+        }
+        if (m_ref == -INFINITY) {
+          m_ref = mx;
+        } else if (mx > m_ref + RESCALE_TAU) {
+          factor = exp2f((m_ref - mx) * LOG2E);
+          m_ref = mx;
+        }
+      }
+      float sum = 0.f;
+      const float mneg = (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32], w[32];
+        ptx::tmem_ld_32x32(s_addr + c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; c += 2) {
+          float pv[2];
+#pragma unroll
+          for (int u = 0; u < 2; ++u) {
+            const float s = __uint_as_float(r[c + u]);
+            float e;
+            if (p.mode == KP_FLASH_SOFTMAX)
+              e = exp2f(__fmaf_rn(s, LOG2E, -mneg));
+            else
+              e = 1.f / (1.f + expf(-s));
+            pv[u] = (j0 + c0 + c + u < p.N) ? e : 0.f;
+          }
+          sum += pv[0] + pv[1];
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(pv[0]), h1 = __float2bfloat16_rn(pv[1]);
+          w[c >> 1] = pack_bf16(h0, h1);
+          w[16 + (c >> 1)] = pack_bf16(__float2bfloat16_rn(pv[0] - __bfloat162float(h0)),
+                                       __float2bfloat16_rn(pv[1] - __bfloat162float(h1)));
+        }
+        ptx::tmem_st_32x32(s_addr + c0, w);
+      }
+      l_run = l_run * factor + sum;
+      if (__any_sync(0xffffffffu, factor != 1.f)) {
+        ptx::mbar_wait(&ctl->pv_done, (i & 1) ^ 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < ocols; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
+          ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster(p_full_leader);
+    }
+    ptx::mbar_wait(&ctl->o_done, 0);
+    ptx::tc_fence_after();
+    const size_t slot = (size_t)strip * p.G + (g < p.G ? g : 0);
+#pragma unroll 1
+    for (int c0 = 0; c0 < ocols; c0 += 32) {
+      uint32_t r[32];
+      ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
+      ptx::tmem_ld_wait();
+      if (g < p.G) {
+        const int k0 = box0 * 64 + c0;
+#pragma unroll
+        for (int c = 0; c < 32; c += 4)
+          if (k0 + c < p.D)
+            *reinterpret_cast<float4*>(p.part_O + slot * p.D + k0 + c) =
+                make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+      }
+    }
+    if (g < p.G && chunk == 0) {
+      p.part_m[slot] = m_ref;
+      p.part_l[slot] = l_run;
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc2(tm, 512);
+}
+
+}  // namespace
+
+// Launch for a plan prepared by kp_flash_umma (split tables / queries, maps).
+int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
+                          int groups_per_chunk, int n_chunks, int n_qt, int n_strips, int tps, int mode, float* part_m,
+                          float* part_l, float* part_O, cudaStream_t st) {
+  UK2 p;
+  p.G = G;
+  p.N = (int)ctx->N;
+  p.D = ctx->D;
+  p.KB = KBs;
+  p.n_tiles = (int)((ctx->N + 127) / 128);
+  p.tiles_per_strip = tps;
+  p.groups_per_chunk = groups_per_chunk;
+  p.mode = mode;
+  p.part_m = part_m;
+  p.part_l = part_l;
+  p.part_O = part_O;
+  static bool configured = false;
+  if (!configured) {
+    KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U2_SMEM));
+    configured = true;
+  }
+  if (n_qt % 2 != 0) KP_FAIL(ctx, KP_EINVAL, "pair kernel needs an even number of query tiles (%d)", n_qt);
+  {
+    int max_clusters = -1;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(n_qt, n_strips, n_chunks);
+    cfg.blockDim = dim3(UT);
+    cfg.dynamicSmemBytes = U2_SMEM;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    static bool reported = false;
+    if (!reported) {
+      cudaError_t e = cudaOccupancyMaxActiveClusters(&max_clusters, flash_umma2_kernel, &cfg);
+      if (e != cudaSuccess || max_clusters <= 0)
+        fprintf(stderr, "kelpie_b200: cudaOccupancyMaxActiveClusters -> %d (%s)\n", max_clusters, cudaGetErrorString(e));
+      cudaGetLastError();
+      reported = true;
+    }
+    KpTimer timer(ctx, kp_ctx::T_FLASH, st);
+    flash_umma2_kernel<<<dim3(n_qt, n_strips, n_chunks), UT, U2_SMEM, st>>>(ctx->um.eh_map, ctx->um.el_map, ctx->um.eh64_map,
+                                                                          ctx->um.el64_map, qh_map, ql_map, p);
+  }
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}

@@ -41,7 +41,8 @@ struct kp_ctx {
   struct {
     bool ready = false;
     void *ent_hi = nullptr, *ent_lo = nullptr;
-    CUtensorMap eh_map, el_map;
+    CUtensorMap eh_map, el_map;      // box {64 bf16, 128 rows}
+    CUtensorMap eh64_map, el64_map;  // box {64 bf16, 64 rows} (half entity tile, cta_group::2 pass)
   } um;
 
   // grow-only device workspace arenas (0: drivers' scratch, 1: the tcgen05 pass's own scratch)
@@ -54,6 +55,7 @@ struct kp_ctx {
   int64_t launches = 0;
   int64_t force_simt = 0;
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
+  int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
   int64_t umma_cq = 0;  // query tiles per cluster of the tcgen05 pass (0 = automatic)
 
   // optional per-category kernel timing (kp_set_option("timing", 1); read with kp_stat)
@@ -177,3 +179,6 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
                          int step = 0);
 int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
              int ldc, cudaStream_t st);
+int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
+                          int groups_per_chunk, int n_chunks, int n_qt, int n_strips, int tps, int mode, float* part_m,
+                          float* part_l, float* part_O, cudaStream_t st);
