@@ -133,6 +133,8 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t ring_a = ptx::smem_u32(ring);
+      // descriptor templates: only the 14-bit start-address field changes between MMAs
+      const uint64_t DK = udesc(0, 16, 1024), DMN = udesc(0, 16384, 1024);
       uint32_t use = 0;
       auto wait_slot = [&](uint32_t u) { ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1); };
       auto release = [&](uint32_t u) { ptx::umma2_commit_mc(&ctl->empty[u % NSLOT], 3); };
@@ -145,9 +147,11 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           const uint32_t e_hi = ring_a + (use % NSLOT) * SLOT, e_lo = e_hi + 16384;
           const uint32_t d_o = TM_O + g * 128;
           const uint32_t p_t = TM_S + (t & 1) * 128;
+          const uint64_t bh = DMN + (e_hi >> 4), bl = DMN + (e_lo >> 4);
+#pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint32_t a_hi = p_t + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
-            const uint64_t b_hi = udesc(e_hi + ks * 2048, 16384, 1024), b_lo = udesc(e_lo + ks * 2048, 16384, 1024);
+            const uint64_t b_hi = bh + ks * (2048 >> 4), b_lo = bl + ks * (2048 >> 4);
             ptx::umma2_bf16_ts(d_o, a_hi, b_hi, idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
             ptx::umma2_bf16_ts(d_o, a_hi, b_lo, idesc_pv, 1u);
             ptx::umma2_bf16_ts(d_o, a_lo, b_hi, idesc_pv, 1u);
@@ -166,12 +170,12 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           ptx::tc_fence_after();
           const uint32_t q_hi = ring_a + (use % NSLOT) * SLOT, q_lo = q_hi + 16384;
           const uint32_t e_hi = ring_a + ((use + 1) % NSLOT) * SLOT, e_lo = e_hi + 8192;
+          const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
+#pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            const uint64_t a_hi = udesc(q_hi + kk * 32, 16, 1024), a_lo = udesc(q_lo + kk * 32, 16, 1024);
-            const uint64_t b_hi = udesc(e_hi + kk * 32, 16, 1024), b_lo = udesc(e_lo + kk * 32, 16, 1024);
-            ptx::umma2_bf16(d_s, a_hi, b_hi, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
-            ptx::umma2_bf16(d_s, a_hi, b_lo, idesc_s, 1u);
-            ptx::umma2_bf16(d_s, a_lo, b_hi, idesc_s, 1u);
+            ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
+            ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
+            ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc_s, 1u);
           }
           release(use);
           release(use + 1);
