@@ -131,3 +131,18 @@ def test_post_trained_rows_golden(kind):
         assert int(res["target_rank"]) == int(r_res[1])
         assert abs(res["target_score"] - r_res[0]) <= RTOL * max(1.0, abs(r_res[0]))
         assert abs(float(res["best_score"]) - r_res[2]) <= RTOL * max(1.0, abs(r_res[2]))
+
+
+@pytest.mark.parametrize("kind", ["TransE", "ComplEx", "ConvE"])
+def test_evaluator_metrics_match_golden_ranks(kind):
+    """Evaluator (evaluation.py:16-48,74-92) over predict_triples: metrics from the reference's ranks."""
+    from kelpie_b200.link_prediction.evaluation import Evaluator
+    z, meta, kg, w, order = load(kind)
+    ds = _dataset(z)
+    m = _model(kind, z, meta, ds)
+    got = Evaluator(m).evaluate(z["predict_q"])
+    ranks = np.concatenate([z["predict_ranks"][:, 1], z["predict_ranks"][:, 0]]).astype(float)
+    assert got["mrr"] == pytest.approx(float(np.mean(1.0 / ranks)))
+    assert got["mr"] == pytest.approx(float(np.mean(ranks)))
+    assert got["h1"] == pytest.approx(float(np.mean(ranks <= 1)))
+    assert got["h10"] == pytest.approx(float(np.mean(ranks <= 10)))
