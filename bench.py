@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--candidates", type=int, default=None, help="override the preset's candidates per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], metavar="NAME=VALUE",
+                    help="kp_set_option knob for A/B runs (e.g. umma_x4=0)")
     args = ap.parse_args()
     cfg = dict(PRESETS[args.workload])
     if args.candidates:
@@ -251,6 +253,9 @@ def main():
 
     ent, rel, conve, D = make_tables(cfg, device)
     ctx = runtime.Context(kind, ent, rel, norm=2, conve=conve, device=local)
+    for kv in args.opt:
+        name, value = kv.split("=")
+        ctx.set_option(name, int(value))
     hp = runtime.make_hp(kind, cfg["hp"])
     arrs, triples, flt_off, flt_ids, jobs, filters = make_batch(cfg, D, C, 1000 + rank)
     mode = runtime.RANK_ENGINE_MIN if kind == "TransE" else runtime.RANK_ENGINE_MAX

@@ -183,6 +183,15 @@ int kp_set_option(kp_ctx* ctx, const char* name, int64_t value);
  * cat in {pass, flash, transe_train, update, conv}.  Synchronises the recorded events. */
 int kp_stat(kp_ctx* ctx, const char* name, double* out);
 
+/* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
+ * n_rows query vectors [n_rows, D] (device) against the resident entity table:
+ *   out_m[g] = max_j z_gj (softmax: the reference max used, >= true max - 8),  out_l[g] = sum_j p_gj,
+ *   out_O[g, :] = sum_j p_gj * E[j, :]   with p = exp(z - out_m) or sigmoid(z),  z = q_g . E[j].
+ * This is the inner contraction of the ComplEx / ConvE post-training steps (SURVEY 9.3/9.4:
+ * logsumexp and delta-a = sum_j G_ij E[j]); the tests check it against an fp64 restatement. */
+int kp_debug_contract(kp_ctx* ctx, int32_t n_rows, const float* queries, int32_t mode, float* out_m,
+                      float* out_l, float* out_O, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -32,6 +32,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_2sm = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_x4")) {
+    ctx->umma_x4 = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "force_tile")) {
     ctx->force_tile = value;
     return KP_OK;

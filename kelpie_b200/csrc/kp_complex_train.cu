@@ -208,7 +208,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
   if (cap > (int64_t)1 << 30) KP_FAIL(ctx, KP_EUNSUPPORTED, "batch too large (%lld rows per step)", (long long)cap);
   const int G = (int)cap;
   const int Gpad = ((G + 63) / 64) * 64;
-  const int S = kp_flash_max_strips(ctx);  // worst case (few rows -> many strips)
+  const size_t SG = kp_flash_part_rows(ctx, G);  // rows of strip partials, worst case over steps of <= G rows
 
   size_t need = 0;
   need += 3 * WsCursor::need((size_t)C * D, 4);         // mim, st1, st2
@@ -216,7 +216,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
   need += 6 * WsCursor::need(G, 4);
   need += 2 * WsCursor::need((size_t)Gpad * D, 4);      // qA, qB
   need += WsCursor::need(G, 4);                          // lseB
-  need += 2 * WsCursor::need((size_t)S * G, 4) + WsCursor::need((size_t)S * G * D, 4);
+  need += 2 * WsCursor::need(SG, 4) + WsCursor::need(SG * D, 4);
   int rc = kp_ws_reserve(ctx, need);
   if (rc != KP_OK) return rc;
   WsCursor ws{ctx->ws, ctx->ws + ctx->ws_bytes};
@@ -233,9 +233,9 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
   float* qA = ws.take<float>((size_t)Gpad * D);
   float* qB = ws.take<float>((size_t)Gpad * D);
   float* lseB = ws.take<float>(G);
-  float* pm = ws.take<float>((size_t)S * G);
-  float* plv = ws.take<float>((size_t)S * G);
-  float* pO = ws.take<float>((size_t)S * G * D);
+  float* pm = ws.take<float>(SG);
+  float* plv = ws.take<float>(SG);
+  float* pO = ws.take<float>(SG * D);
 
   KP_CUDA(ctx, cudaMemcpyAsync(mim, b->init_rows, (size_t)C * D * 4, cudaMemcpyDeviceToDevice, st));
   KP_CUDA(ctx, cudaMemsetAsync(st1, 0, (size_t)C * D * 4, st));

@@ -208,12 +208,12 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   if (cap < 1) cap = 1;
   if (cap > (int64_t)1 << 28) KP_FAIL(ctx, KP_EUNSUPPORTED, "batch too large (%lld pairs per step)", (long long)cap);
   const int G = (int)cap, Gpad = ((G + 63) / 64) * 64;
-  const int S = kp_flash_max_strips(ctx);
+  const size_t SG = kp_flash_part_rows(ctx, G);  // rows of strip partials, worst case over steps of <= G rows
 
   size_t need = 3 * WsCursor::need((size_t)C * D, 4) + 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8) +
                 7 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
                 2 * WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
-                2 * WsCursor::need((size_t)S * G, 4) + WsCursor::need((size_t)S * G * D, 4);
+                2 * WsCursor::need(SG, 4) + WsCursor::need(SG * D, 4);
   int rc = kp_ws_reserve(ctx, need);
   if (rc != KP_OK) return rc;
   WsCursor ws{ctx->ws, ctx->ws + ctx->ws_bytes};
@@ -234,9 +234,9 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   float* dh = ws.take<float>((size_t)G * D);
   float* glhs = ws.take<float>((size_t)G * D);
   float* colcoef = ws.take<float>(G);
-  float* pm = ws.take<float>((size_t)S * G);
-  float* plv = ws.take<float>((size_t)S * G);
-  float* pO = ws.take<float>((size_t)S * G * D);
+  float* pm = ws.take<float>(SG);
+  float* plv = ws.take<float>(SG);
+  float* pO = ws.take<float>(SG * D);
 
   KP_CUDA(ctx, cudaMemcpyAsync(mim, b->init_rows, (size_t)C * D * 4, cudaMemcpyDeviceToDevice, st));
   KP_CUDA(ctx, cudaMemsetAsync(st1, 0, (size_t)C * D * 4, st));

@@ -246,6 +246,19 @@ int kp_flash_max_strips(kp_ctx* ctx) {
   return a > b ? a : b;
 }
 
+// Upper bound on n_strips(g) * g over every row count g <= G a caller may run the pass with:
+// CUDA-core path (g < 32), tcgen05 path with CTAs <= SMs (strips * query tiles <= SMs) and with
+// more CTAs than SMs (<= 8 strips, chosen against wave quantisation).
+size_t kp_flash_part_rows(kp_ctx* ctx, int G) {
+  int a = 1;
+  kp_flash_plan(ctx, 16, &a);
+  size_t rows = (size_t)a * (size_t)(G < 32 ? G : 32);
+  const size_t few = (size_t)64 * G < (size_t)ctx->sm_count * 128 ? (size_t)64 * G : (size_t)ctx->sm_count * 128;
+  if (few > rows) rows = few;
+  if ((size_t)8 * G > rows) rows = (size_t)8 * G;
+  return rows + (size_t)G;  // slack for the CUDA-core plan's rounding (strips = ceil(2 SMs / query tiles))
+}
+
 int kp_flash_run(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
                  cudaStream_t st, int* n_strips) {
   if (kp_flash_umma_usable(ctx, G)) {
@@ -254,4 +267,64 @@ int kp_flash_run(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m,
   }
   kp_flash_plan(ctx, G, n_strips);
   return kp_flash_simt(ctx, qmat, G, mode, part_m, part_l, part_O, st);
+}
+
+// ---- diagnostic entry: the fused pass alone (tests compare it with an fp64 restatement) ----------
+namespace {
+__global__ void flash_merge_kernel(const float* part_m, const float* part_l, const float* part_O, int n_strips, int G, int D,
+                                   int mode, float* out_m, float* out_l, float* out_O) {
+  const int g = blockIdx.x;
+  float M, L;
+  if (mode == KP_FLASH_SIGMOID) {  // no normaliser: strips simply add
+    L = 0.f;
+    for (int s = 0; s < n_strips; ++s) L += part_l[(size_t)s * G + g];
+    if (threadIdx.x == 0) {
+      out_m[g] = 0.f;
+      out_l[g] = L;
+    }
+    for (int k = threadIdx.x; k < D; k += blockDim.x) {
+      float acc = 0.f;
+      for (int s = 0; s < n_strips; ++s) acc += part_O[((size_t)s * G + g) * D + k];
+      out_O[(size_t)g * D + k] = acc;
+    }
+    return;
+  }
+  kp_flash_merge_stats(part_m, part_l, n_strips, G, g, M, L);
+  if (threadIdx.x == 0) {
+    out_m[g] = M;
+    out_l[g] = L;
+  }
+  for (int k = threadIdx.x; k < D; k += blockDim.x) {
+    float acc = 0.f;
+    for (int s = 0; s < n_strips; ++s) {
+      const float m = part_m[(size_t)s * G + g];
+      if (m != -INFINITY) acc += part_O[((size_t)s * G + g) * D + k] * expf(m - M);
+    }
+    out_O[(size_t)g * D + k] = acc;
+  }
+}
+}  // namespace
+
+extern "C" int kp_debug_contract(kp_ctx* ctx, int32_t n_rows, const float* queries, int32_t mode, float* out_m, float* out_l,
+                                 float* out_O, void* stream) {
+  if (!ctx || n_rows <= 0 || !queries || !out_m || !out_l || !out_O) return KP_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int G = n_rows, D = ctx->D;
+  const size_t SG = kp_flash_part_rows(ctx, G);
+  const size_t Gpad = ((size_t)G + 127) / 128 * 128;
+  size_t need = WsCursor::need(Gpad * D, 4) + 2 * WsCursor::need(SG, 4) + WsCursor::need(SG * D, 4);
+  int rc = kp_ws_reserve(ctx, need);
+  if (rc != KP_OK) return rc;
+  WsCursor ws{ctx->ws, ctx->ws + ctx->ws_bytes};
+  float* q = ws.take<float>(Gpad * D);
+  float* pm = ws.take<float>(SG);
+  float* pl = ws.take<float>(SG);
+  float* pO = ws.take<float>(SG * D);
+  KP_CUDA(ctx, cudaMemsetAsync(q, 0, Gpad * D * 4, st));
+  KP_CUDA(ctx, cudaMemcpyAsync(q, queries, (size_t)G * D * 4, cudaMemcpyDeviceToDevice, st));
+  int n_strips = 1;
+  if ((rc = kp_flash_run(ctx, q, G, mode, pm, pl, pO, st, &n_strips)) != KP_OK) return rc;
+  flash_merge_kernel<<<G, 128, 0, st>>>(pm, pl, pO, n_strips, G, D, mode, out_m, out_l, out_O);
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
 }

@@ -20,6 +20,7 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
 int kp_flash_run(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
                  cudaStream_t st, int* n_strips);
 int kp_flash_max_strips(kp_ctx* ctx);
+size_t kp_flash_part_rows(kp_ctx* ctx, int G);
 
 #ifdef __CUDACC__
 // Merge the per-strip softmax statistics of row g: returns M = max_s m_s and L = sum_s l_s e^{m_s-M}.

@@ -28,13 +28,13 @@
 #include "kp_flash.cuh"
 #include "kp_internal.h"
 #include "kp_ptx.cuh"
+#include "kp_umma_softmax.cuh"
 
 namespace {
 
 constexpr int UT = 192;               // threads
 constexpr int SLOT = 32768;           // {hi 16 KB | lo 16 KB}
 constexpr int NSLOT = 6;
-constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_TAU = 8.0f;   // rescale O only when the row max grew by more than this
 
 struct UCtl {
@@ -237,56 +237,11 @@ flash_umma_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_const
       ptx::mbar_wait(&ctl->s_full[sb], (i >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t s_addr = TM_S + sb * 128 + lane_off;
-      float factor = 1.f;
-      if (p.mode == KP_FLASH_SOFTMAX) {
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(s_addr + c0, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (j0 + c0 + c < p.N) mx = fmaxf(mx, __uint_as_float(r[c]));
-        }
-        if (m_ref == -INFINITY) {
-          m_ref = mx;
-        } else if (mx > m_ref + RESCALE_TAU) {
-          factor = exp2f((m_ref - mx) * LOG2E);
-          m_ref = mx;
-        }
-      }
-      // P(i) = exp(S - m_ref) (or sigmoid), split into bf16 hi/lo and written over the S chunk it
-      // came from; this overlaps PV(i-1) and S(i+1) on the tensor pipe.
-      float sum = 0.f;
-      const float mneg = (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r[32], w[32];
-        ptx::tmem_ld_32x32(s_addr + c0, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float s = __uint_as_float(r[c + u]);
-            float e;
-            if (p.mode == KP_FLASH_SOFTMAX)
-              e = exp2f(__fmaf_rn(s, LOG2E, -mneg));
-            else
-              e = 1.f / (1.f + expf(-s));
-            pv[u] = (j0 + c0 + c + u < p.N) ? e : 0.f;
-          }
-          sum += pv[0] + pv[1];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(pv[0]), h1 = __float2bfloat16_rn(pv[1]);
-          w[c >> 1] = pack_bf16(h0, h1);
-          w[16 + (c >> 1)] = pack_bf16(__float2bfloat16_rn(pv[0] - __bfloat162float(h0)),
-                                       __float2bfloat16_rn(pv[1] - __bfloat162float(h1)));
-        }
-        ptx::tmem_st_32x32(s_addr + c0, w);
-      }
-      l_run = l_run * factor + sum;
+      float factor;
+      if (p.mode == KP_FLASH_SOFTMAX)
+        umma_sm::p_tile<true>(s_addr, j0, p.N, RESCALE_TAU, m_ref, l_run, factor);
+      else
+        umma_sm::p_tile<false>(s_addr, j0, p.N, RESCALE_TAU, m_ref, l_run, factor);
       if (__any_sync(0xffffffffu, factor != 1.f)) {
         // O holds tiles < i only once PV(i-1) has completed
         ptx::mbar_wait(&ctl->pv_done, (i & 1) ^ 1);
@@ -372,6 +327,7 @@ struct UPlan {
   int n_qt;    // query tiles, padded to a multiple of cq
   int n_strips, n_tiles, tps;
   bool pair;   // cta_group::2 kernel (kp_flash_umma2.cu): SM pairs over 2 query tiles
+  bool quad;   // clusters of two pairs sharing S across the dim chunks (kp_flash_umma4.cu)
 };
 UPlan umma_plan(kp_ctx* ctx, int G) {
   UPlan u;
@@ -391,8 +347,26 @@ UPlan umma_plan(kp_ctx* ctx, int G) {
   u.cq = cq;
   u.n_qt = ((n_qt + cq - 1) / cq) * cq;
   u.n_tiles = (int)((ctx->N + 127) / 128);
-  int s = ctx->sm_count / (u.n_qt * u.cc);
+  u.quad = u.pair && u.cc == 2 && ctx->umma_x4 != 0;
+  const int sms = u.quad ? kp_flash_umma4_sms(ctx) : ctx->sm_count;
+  int s = sms / (u.n_qt * u.cc);
   if (s > 64) s = 64;
+  if (s < 1) {
+    // more CTAs than SMs: pick the strip count (<= 8) whose last wave is fullest
+    const int unit = u.quad ? 4 : (u.pair ? 2 : 1);           // CTAs that must be co-resident
+    const long long units = (long long)u.n_qt * u.cc / unit;  // per strip
+    const long long slots = sms / unit;
+    double best = 0.0;
+    s = 1;
+    for (int c = 1; c <= 8; ++c) {
+      const long long waves = (units * c + slots - 1) / slots;
+      const double eff = (double)(units * c) / (double)(waves * slots);
+      if (eff > best + 0.02) {
+        best = eff;
+        s = c;
+      }
+    }
+  }
   if (s > u.n_tiles) s = u.n_tiles;
   if (s < 1) s = 1;
   u.tps = (u.n_tiles + s - 1) / s;
@@ -441,6 +415,9 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   if ((rc = encode_bf16(ctx, &qh_map, qh, Gpad, Dpad)) != KP_OK) return rc;
   if ((rc = encode_bf16(ctx, &ql_map, ql, Gpad, Dpad)) != KP_OK) return rc;
 
+  if (u.quad)
+    return kp_flash_umma4_launch(ctx, qh_map, ql_map, G, u.KBs, u.bpc / 2, u.n_qt, u.n_strips, u.tps, mode, part_m, part_l,
+                                 part_O, st);
   if (u.pair)
     return kp_flash_umma2_launch(ctx, qh_map, ql_map, G, u.KBs, u.bpc / 2, u.cc, u.n_qt, u.n_strips, u.tps, mode, part_m,
                                  part_l, part_O, st);

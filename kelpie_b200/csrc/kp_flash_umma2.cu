@@ -16,13 +16,13 @@
 #include "kp_flash.cuh"
 #include "kp_internal.h"
 #include "kp_ptx.cuh"
+#include "kp_umma_softmax.cuh"
 
 namespace {
 
 constexpr int UT = 192;
 constexpr int SLOT = 32768;
 constexpr int NSLOT = 6;
-constexpr float LOG2E = 1.4426950408889634f;
 constexpr float RESCALE_TAU = 8.0f;
 
 struct UCtl2 {
@@ -48,9 +48,6 @@ __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, ui
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
-}
-__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
-  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(UT, 1)
@@ -202,54 +199,11 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       ptx::mbar_wait(&ctl->s_full[sb], (i >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t s_addr = TM_S + sb * 128 + lane_off;
-      float factor = 1.f;
-      if (p.mode == KP_FLASH_SOFTMAX) {
-        float mx = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < 128; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(s_addr + c0, r);
-          ptx::tmem_ld_wait();
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (j0 + c0 + c < p.N) mx = fmaxf(mx, __uint_as_float(r[c]));
-        }
-        if (m_ref == -INFINITY) {
-          m_ref = mx;
-        } else if (mx > m_ref + RESCALE_TAU) {
-          factor = exp2f((m_ref - mx) * LOG2E);
-          m_ref = mx;
-        }
-      }
-      float sum = 0.f;
-      const float mneg = (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
-#pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
-        uint32_t r[32], w[32];
-        ptx::tmem_ld_32x32(s_addr + c0, r);
-        ptx::tmem_ld_wait();
-#pragma unroll
-        for (int c = 0; c < 32; c += 2) {
-          float pv[2];
-#pragma unroll
-          for (int u = 0; u < 2; ++u) {
-            const float s = __uint_as_float(r[c + u]);
-            float e;
-            if (p.mode == KP_FLASH_SOFTMAX)
-              e = exp2f(__fmaf_rn(s, LOG2E, -mneg));
-            else
-              e = 1.f / (1.f + expf(-s));
-            pv[u] = (j0 + c0 + c + u < p.N) ? e : 0.f;
-          }
-          sum += pv[0] + pv[1];
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(pv[0]), h1 = __float2bfloat16_rn(pv[1]);
-          w[c >> 1] = pack_bf16(h0, h1);
-          w[16 + (c >> 1)] = pack_bf16(__float2bfloat16_rn(pv[0] - __bfloat162float(h0)),
-                                       __float2bfloat16_rn(pv[1] - __bfloat162float(h1)));
-        }
-        ptx::tmem_st_32x32(s_addr + c0, w);
-      }
-      l_run = l_run * factor + sum;
+      float factor;
+      if (p.mode == KP_FLASH_SOFTMAX)
+        umma_sm::p_tile<true>(s_addr, j0, p.N, RESCALE_TAU, m_ref, l_run, factor);
+      else
+        umma_sm::p_tile<false>(s_addr, j0, p.N, RESCALE_TAU, m_ref, l_run, factor);
       if (__any_sync(0xffffffffu, factor != 1.f)) {
         ptx::mbar_wait(&ctl->pv_done, (i & 1) ^ 1);
         ptx::tc_fence_after();

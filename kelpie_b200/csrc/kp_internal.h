@@ -56,6 +56,7 @@ struct kp_ctx {
   int64_t force_simt = 0;
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
+  int64_t umma_x4 = 1;   // rows wider than 256 floats: clusters of two pairs that compute S once (kp_flash_umma4.cu)
   int64_t umma_cq = 0;  // query tiles per cluster of the tcgen05 pass (0 = automatic)
 
   // optional per-category kernel timing (kp_set_option("timing", 1); read with kp_stat)
@@ -182,3 +183,7 @@ int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int 
 int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
                           int groups_per_chunk, int n_chunks, int n_qt, int n_strips, int tps, int mode, float* part_m,
                           float* part_l, float* part_O, cudaStream_t st);
+int kp_flash_umma4_sms(kp_ctx* ctx);
+int kp_flash_umma4_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
+                          int groups_per_chunk, int n_qt, int n_strips, int tps, int mode, float* part_m, float* part_l,
+                          float* part_O, cudaStream_t st);

@@ -21,6 +21,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkelpie_
 EXPORTS = [
     "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
     "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
+    "kp_debug_contract",
 ]
 
 
@@ -88,6 +89,8 @@ def load_library():
     lib.kp_set_option.restype = c_int
     lib.kp_stat.argtypes = [c_void_p, c_char_p, POINTER(ctypes.c_double)]
     lib.kp_stat.restype = c_int
+    lib.kp_debug_contract.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.kp_debug_contract.restype = c_int
     _lib = lib
     return lib
 
@@ -223,6 +226,17 @@ class Context:
                                               _ptr(ts), _ptr(bs), _ptr(rk), _ptr(cn), self._stream()),
                     "kp_filtered_rank")
         return (ts, bs, rk, cn) if counters else (ts, bs, rk)
+
+    def contract(self, queries, mode=0):
+        """Diagnostic: fused score -> softmax (0) / sigmoid (1) -> contract pass; returns (m[G], l[G], O[G,D])."""
+        q = self.dev(queries, torch.float32).view(-1, self.D).contiguous()
+        G = q.shape[0]
+        m = torch.empty(G, dtype=torch.float32, device=self.device)
+        l = torch.empty(G, dtype=torch.float32, device=self.device)
+        O = torch.empty((G, self.D), dtype=torch.float32, device=self.device)
+        self._check(self.lib.kp_debug_contract(self.handle, G, _ptr(q), int(mode), _ptr(m), _ptr(l), _ptr(O),
+                                               self._stream()), "kp_debug_contract")
+        return m, l, O
 
     def post_train(self, hp, init_rows, row_off, rows_per_epoch, pos, neg=None, pos_off=None, pos_ids=None,
                    static_epochs=False, dropout_seed=0, max_rows_per_epoch=None, total_rows=None):
