@@ -36,6 +36,17 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_x4 = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_prof")) {
+    if (value && !ctx->umma_prof) {
+      void* d = nullptr;
+      if (cudaMalloc(&d, 4 * sizeof(unsigned long long)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "umma_prof counters");
+      cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+      ctx->owned.push_back(d);
+      ctx->umma_prof = static_cast<unsigned long long*>(d);
+    }
+    if (!value) ctx->umma_prof = nullptr;
+    return KP_OK;
+  }
   if (!strcmp(name, "force_tile")) {
     ctx->force_tile = value;
     return KP_OK;
@@ -79,6 +90,16 @@ extern "C" int kp_stat(kp_ctx* ctx, const char* name, double* out) {
   for (int i = 0; i < kp_ctx::T_NCAT; ++i) {
     if (!strncmp(name, "ms_", 3) && !strcmp(name + 3, cats[i])) { *out = ctx->t_ms[i]; return KP_OK; }
     if (!strncmp(name, "n_", 2) && !strcmp(name + 2, cats[i])) { *out = (double)ctx->t_n[i]; return KP_OK; }
+  }
+  if (!strncmp(name, "umma_prof_", 10) && ctx->umma_prof) {  // slot / own / for / total (MMA-thread cycles, summed over pairs)
+    static const char* w[] = {"slot", "own", "for", "total"};
+    for (int i = 0; i < 4; ++i)
+      if (!strcmp(name + 10, w[i])) {
+        unsigned long long v = 0;
+        KP_CUDA(ctx, cudaMemcpy(&v, ctx->umma_prof + i, sizeof(v), cudaMemcpyDeviceToHost));
+        *out = (double)v;
+        return KP_OK;
+      }
   }
   KP_FAIL(ctx, KP_EINVAL, "unknown stat '%s'", name);
 }

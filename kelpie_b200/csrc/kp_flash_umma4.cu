@@ -53,6 +53,7 @@ struct UK4 {
   float* part_m;
   float* part_l;
   float* part_O;
+  unsigned long long* prof;  // optional [4]: MMA-thread cycles waiting on TMA slots / own P / foreign P, total
 };
 
 __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -74,11 +75,13 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   return v;
 }
 
-// Own tile: S (TMEM A) -> P, written back over S and sent to the peer CTA (pin_row = cluster address
-// of this row's first chunk in the peer's message buffer).  Same arithmetic as umma_sm::p_tile.
+// Own tile: S (TMEM A) -> P, written back over S; the packed words stay in w[128] so that the caller
+// can release the MMA warp first and ship the tile to the peer CTA afterwards (a 64 KB tile takes
+// ~3000 cycles through distributed shared memory -- off the S -> softmax -> PV critical path).
+// Same arithmetic as umma_sm::p_tile.
 template <bool SOFTMAX>
-__device__ __forceinline__ void p_tile_send(uint32_t s_addr, int j0, int N, float tau, float& m_ref, float& l_run,
-                                            float& factor, uint32_t pin_row, uint64_t* pin_empty, int k) {
+__device__ __forceinline__ void p_tile_own(uint32_t s_addr, int j0, int N, float tau, float& m_ref, float& l_run,
+                                           float& factor, float& sum, uint32_t (&w)[128]) {
   using namespace umma_sm;
   uint32_t r[128];
 #pragma unroll
@@ -107,12 +110,9 @@ __device__ __forceinline__ void p_tile_send(uint32_t s_addr, int j0, int N, floa
     }
     mneg = (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
   }
-  // the peer has consumed my previous message (normally long ago: it gates the peer's own next tile)
-  if (k > 0) ptx::mbar_wait_cluster(pin_empty, (k - 1) & 1);
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
-    uint32_t w[32];
 #pragma unroll
     for (int c = 0; c < 32; c += 2) {
       float p0, p1;
@@ -126,15 +126,12 @@ __device__ __forceinline__ void p_tile_send(uint32_t s_addr, int j0, int N, floa
       sum0 += p0;
       sum1 += p1;
       const uint32_t hi = bf16x2(p0, p1);
-      w[c >> 1] = hi;
-      w[16 + (c >> 1)] = bf16x2(p0 - __uint_as_float(hi << 16), p1 - __uint_as_float(hi & 0xffff0000u));
+      w[32 * q + (c >> 1)] = hi;
+      w[32 * q + 16 + (c >> 1)] = bf16x2(p0 - __uint_as_float(hi << 16), p1 - __uint_as_float(hi & 0xffff0000u));
     }
-    ptx::tmem_st_32x32(s_addr + 32 * q, w);
-#pragma unroll
-    for (int v = 0; v < 8; ++v) st_cluster_v4(pin_row + (uint32_t)(8 * q + v) * 2048u, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
+    ptx::tmem_st_32x32(s_addr + 32 * q, reinterpret_cast<uint32_t(&)[32]>(w[32 * q]));
   }
-  const float sum = sum0 + sum1;
-  st_cluster_v4(pin_row + 32u * 2048u, __float_as_uint(m_ref), __float_as_uint(factor), __float_as_uint(sum), 0u);
+  sum = sum0 + sum1;
   l_run = l_run * factor + sum;
 }
 
@@ -234,7 +231,14 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       const uint32_t ring_a = ptx::smem_u32(ring);
       const uint64_t DK = udesc(0, 16, 1024), DMN = udesc(0, 16384, 1024);
       uint32_t use = 0;
-      auto wait_slot = [&](uint32_t u) { ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1); };
+      long long w_slot = 0, w_own = 0, w_for = 0;
+      const long long t_begin = clock64();
+      auto wait_slot = [&](uint32_t u) {
+        if (ptx::mbar_try_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1)) return;
+        const long long a = clock64();
+        ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1);
+        w_slot += clock64() - a;
+      };
       auto release = [&](uint32_t u) { ptx::umma2_commit_mc(&ctl->empty[u % NSLOT], pair_mask); };
       auto mma_s = [&](int t) {
         for (int kb = 0; kb < p.KB; ++kb) {
@@ -259,7 +263,11 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       auto mma_pv = [&](int t) {
         const bool own = (t & 1) == par;
         const int k = t >> 1;
-        ptx::mbar_wait_cluster(own ? &ctl->p_own : &ctl->p_for, k & 1);
+        {
+          const long long a = clock64();
+          ptx::mbar_wait_cluster(own ? &ctl->p_own : &ctl->p_for, k & 1);
+          (own ? w_own : w_for) += clock64() - a;
+        }
         ptx::tc_fence_after();
         const uint32_t p_t = own ? TM_A : TM_B;
         for (int g = 0; g < ngroup; ++g) {
@@ -287,6 +295,12 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
         mma_pv(t);
       }
       ptx::umma2_commit_mc(&ctl->o_done, pair_mask);
+      if (p.prof) {
+        atomicAdd(p.prof + 0, (unsigned long long)w_slot);
+        atomicAdd(p.prof + 1, (unsigned long long)w_own);
+        atomicAdd(p.prof + 2, (unsigned long long)w_for);
+        atomicAdd(p.prof + 3, (unsigned long long)(clock64() - t_begin));
+      }
     }
   } else {
     // ------------------------------- softmax / exchange / epilogue (every CTA, own rows) -------------------------------
@@ -302,6 +316,23 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
     const uint32_t pin_empty_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_empty), peer);
     float m_ref = -INFINITY, l_run = 0.f;
     const int ocols = ngroup * 128;
+    // lazy rescale of O before tile t is contracted (rare; never for t = 0): O holds tiles < t only
+    // once PV(t-1) has completed
+    auto rescale_o = [&](int t, float factor) {
+      if (!__any_sync(0xffffffffu, factor != 1.f)) return;
+      const bool prev_own = ((t - 1) & 1) == par;
+      ptx::mbar_wait(prev_own ? &ctl->opv_done : &ctl->fpv_done, ((t - 1) >> 1) & 1);
+      ptx::tc_fence_after();
+#pragma unroll 1
+      for (int c0 = 0; c0 < ocols; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
+        ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
+      }
+    };
     for (int t = 0; t < ntile; ++t) {
       const bool own = (t & 1) == par;
       const int k = t >> 1;
@@ -310,24 +341,25 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
         ptx::mbar_wait(&ctl->s_full, k & 1);
         ptx::tc_fence_after();
         const int j0 = (t0 + t) * 128;
+        uint32_t w[128];
+        float sum;
         if (p.mode == KP_FLASH_SOFTMAX)
-          p_tile_send<true>(TM_A + lane_off, j0, p.N, RESCALE_TAU, m_ref, l_run, factor, pin_peer, &ctl->pin_empty, k);
+          p_tile_own<true>(TM_A + lane_off, j0, p.N, RESCALE_TAU, m_ref, l_run, factor, sum, w);
         else
-          p_tile_send<false>(TM_A + lane_off, j0, p.N, RESCALE_TAU, m_ref, l_run, factor, pin_peer, &ctl->pin_empty, k);
+          p_tile_own<false>(TM_A + lane_off, j0, p.N, RESCALE_TAU, m_ref, l_run, factor, sum, w);
+        rescale_o(t, factor);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive_cluster(p_own_lead);  // PV(t) may start
+        // ship the tile: the peer has consumed my previous message (it gates the peer's own next tile)
+        if (k > 0) ptx::mbar_wait_cluster(&ctl->pin_empty, (k - 1) & 1);
+        st_cluster_v4(pin_peer + 32u * 2048u, __float_as_uint(m_ref), __float_as_uint(factor), __float_as_uint(sum), 0u);
+#pragma unroll
+        for (int v = 0; v < 32; ++v) st_cluster_v4(pin_peer + (uint32_t)v * 2048u, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
         ptx::mbar_arrive_cluster(pin_full_peer);  // release: my row of the message is complete
       } else {
         ptx::mbar_wait_cluster(&ctl->pin_full, k & 1);
-        uint32_t w[128];
-#pragma unroll
-        for (int q = 0; q < 32; ++q) {
-          const uint4 v = ld_shared_v4(pin_local + (uint32_t)q * 2048u);
-          w[4 * q] = v.x;
-          w[4 * q + 1] = v.y;
-          w[4 * q + 2] = v.z;
-          w[4 * q + 3] = v.w;
-        }
         const uint4 h = ld_shared_v4(pin_local + 32u * 2048u);
-        ptx::mbar_arrive_cluster(pin_empty_peer);  // release: the buffer may be overwritten
         m_ref = __uint_as_float(h.x);
         factor = __uint_as_float(h.y);
         l_run = l_run * factor + __uint_as_float(h.z);
@@ -336,26 +368,24 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           ptx::tc_fence_after();
         }
 #pragma unroll
-        for (int q = 0; q < 4; ++q) ptx::tmem_st_32x32(TM_B + lane_off + 32 * q, reinterpret_cast<uint32_t(&)[32]>(w[32 * q]));
-      }
-      if (__any_sync(0xffffffffu, factor != 1.f)) {
-        // O holds tiles < t only once PV(t-1) has completed (t >= 1 here: the first tile never rescales)
-        const bool prev_own = ((t - 1) & 1) == par;
-        ptx::mbar_wait(prev_own ? &ctl->opv_done : &ctl->fpv_done, ((t - 1) >> 1) & 1);
-        ptx::tc_fence_after();
-#pragma unroll 1
-        for (int c0 = 0; c0 < ocols; c0 += 32) {
-          uint32_t r[32];
-          ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
-          ptx::tmem_ld_wait();
+        for (int q = 0; q < 4; ++q) {
+          uint32_t w[32];
 #pragma unroll
-          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
-          ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
+          for (int v = 0; v < 8; ++v) {
+            const uint4 x = ld_shared_v4(pin_local + (uint32_t)(8 * q + v) * 2048u);
+            w[4 * v] = x.x;
+            w[4 * v + 1] = x.y;
+            w[4 * v + 2] = x.z;
+            w[4 * v + 3] = x.w;
+          }
+          ptx::tmem_st_32x32(TM_B + lane_off + 32 * q, w);
         }
+        ptx::mbar_arrive_cluster(pin_empty_peer);  // release: the buffer may be overwritten
+        rescale_o(t, factor);
+        ptx::tmem_st_wait();
+        ptx::tc_fence_before();
+        ptx::mbar_arrive_cluster(p_for_lead);
       }
-      ptx::tmem_st_wait();
-      ptx::tc_fence_before();
-      ptx::mbar_arrive_cluster(own ? p_own_lead : p_for_lead);
     }
     ptx::mbar_wait(&ctl->o_done, 0);
     ptx::tc_fence_after();
@@ -429,6 +459,7 @@ int kp_flash_umma4_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;
+  p.prof = ctx->umma_prof;
   static bool configured = false;
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U4_SMEM));

@@ -1,0 +1,36 @@
+"""Time the fused pass alone (kp_debug_contract) on a config-5-shaped table and print where the MMA
+thread of the cluster-4 kernel waits (option umma_prof)."""
+import sys, os, argparse
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from kelpie_b200 import runtime
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--N", type=int, default=1_000_000)
+ap.add_argument("--D", type=int, default=512)
+ap.add_argument("--G", type=int, default=16896)
+ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--opt", action="append", default=[])
+a = ap.parse_args()
+torch.manual_seed(0)
+ent = (torch.randn(a.N, a.D, device="cuda") * 0.1)
+q = (torch.randn(a.G, a.D, device="cuda") * 0.1)
+ctx = runtime.Context("ComplEx", ent, torch.zeros(2, a.D, device="cuda"))
+for kv in a.opt:
+    n, v = kv.split("="); ctx.set_option(n, int(v))
+ctx.contract(q, 0); torch.cuda.synchronize()
+ctx.set_option("umma_prof", 1)
+ctx.set_option("timing", 1); ctx.stat("reset")
+for _ in range(a.reps):
+    ctx.contract(q, 0)
+torch.cuda.synchronize()
+ms = ctx.stat("ms_flash") / ctx.stat("n_flash")
+fl = 4.0 * a.G * a.N * a.D
+out = {"ms": ms, "tflops_alg": fl / ms / 1e9}
+try:
+    tot = ctx.stat("umma_prof_total")
+    for k in ("slot", "own", "for"):
+        out["wait_" + k] = ctx.stat("umma_prof_" + k) / max(tot, 1)
+except RuntimeError:
+    pass
+print(out)
