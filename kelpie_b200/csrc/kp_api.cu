@@ -39,8 +39,8 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
   if (!strcmp(name, "umma_prof")) {
     if (value && !ctx->umma_prof) {
       void* d = nullptr;
-      if (cudaMalloc(&d, 4 * sizeof(unsigned long long)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "umma_prof counters");
-      cudaMemset(d, 0, 4 * sizeof(unsigned long long));
+      if (cudaMalloc(&d, 16 * sizeof(unsigned long long)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "umma_prof counters");
+      cudaMemset(d, 0, 16 * sizeof(unsigned long long));
       ctx->owned.push_back(d);
       ctx->umma_prof = static_cast<unsigned long long*>(d);
     }
@@ -92,8 +92,8 @@ extern "C" int kp_stat(kp_ctx* ctx, const char* name, double* out) {
     if (!strncmp(name, "n_", 2) && !strcmp(name + 2, cats[i])) { *out = (double)ctx->t_n[i]; return KP_OK; }
   }
   if (!strncmp(name, "umma_prof_", 10) && ctx->umma_prof) {  // slot / own / for / total (MMA-thread cycles, summed over pairs)
-    static const char* w[] = {"slot", "own", "for", "total"};
-    for (int i = 0; i < 4; ++i)
+    static const char* w[] = {"slot", "own", "for", "total", "send", "wpin", "whdr", "wsfull", "soft"};
+    for (int i = 0; i < 9; ++i)
       if (!strcmp(name + 10, w[i])) {
         unsigned long long v = 0;
         KP_CUDA(ctx, cudaMemcpy(&v, ctx->umma_prof + i, sizeof(v), cudaMemcpyDeviceToHost));

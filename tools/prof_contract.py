@@ -10,6 +10,7 @@ ap.add_argument("--N", type=int, default=1_000_000)
 ap.add_argument("--D", type=int, default=512)
 ap.add_argument("--G", type=int, default=16896)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--mode", type=int, default=0)
 ap.add_argument("--opt", action="append", default=[])
 a = ap.parse_args()
 torch.manual_seed(0)
@@ -18,18 +19,22 @@ q = (torch.randn(a.G, a.D, device="cuda") * 0.1)
 ctx = runtime.Context("ComplEx", ent, torch.zeros(2, a.D, device="cuda"))
 for kv in a.opt:
     n, v = kv.split("="); ctx.set_option(n, int(v))
-ctx.contract(q, 0); torch.cuda.synchronize()
+ctx.contract(q, a.mode); torch.cuda.synchronize()
+torch.cuda.synchronize()
 ctx.set_option("umma_prof", 1)
 ctx.set_option("timing", 1); ctx.stat("reset")
 for _ in range(a.reps):
-    ctx.contract(q, 0)
+    ctx.contract(q, a.mode)
 torch.cuda.synchronize()
 ms = ctx.stat("ms_flash") / ctx.stat("n_flash")
 fl = 4.0 * a.G * a.N * a.D
 out = {"ms": ms, "tflops_alg": fl / ms / 1e9}
 try:
     tot = ctx.stat("umma_prof_total")
-    for k in ("slot", "own", "for"):
+    n_qt = (a.G + 255) // 256 * 2
+    out["cycles_per_pair"] = tot / (n_qt * (a.reps + 0))  # pairs = 2 per cluster = n_qt (one per query tile)
+    out["sm_mhz_in_kernel"] = out["cycles_per_pair"] / ms / 1e3
+    for k in ("slot", "own", "for", "send", "wpin", "whdr", "wsfull", "soft"):
         out["wait_" + k] = ctx.stat("umma_prof_" + k) / max(tot, 1)
 except RuntimeError:
     pass
