@@ -36,6 +36,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_x4 = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_rotate")) {
+    ctx->umma_rotate = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "umma_prof")) {
     if (value && !ctx->umma_prof) {
       void* d = nullptr;

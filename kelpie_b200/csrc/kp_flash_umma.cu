@@ -402,6 +402,11 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
     if ((rc = kp_encode_2d(ctx, &ctx->um.el64_map, l, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
     ctx->um.ent_hi = h;
     ctx->um.ent_lo = l;
+    void* cur = nullptr;
+    if (cudaMalloc(&cur, 64 * sizeof(int)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "cannot allocate the walk cursors");
+    ctx->owned.push_back(cur);
+    KP_CUDA(ctx, cudaMemsetAsync(cur, 0, 64 * sizeof(int), st));
+    ctx->umma_cursor = static_cast<int*>(cur);
     ctx->um.ready = true;
   }
   const long long Gpad = (long long)u.n_qt * 128;

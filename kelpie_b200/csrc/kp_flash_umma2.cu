@@ -30,6 +30,7 @@ struct UCtl2 {
   uint64_t s_full[2];
   uint64_t p_full, pv_done, o_done;
   uint32_t tmem_base;
+  int start, start_local;
 };
 constexpr size_t U2_SMEM = (size_t)NSLOT * SLOT + sizeof(UCtl2) + 1024;
 
@@ -38,6 +39,7 @@ struct UK2 {
   float* part_m;
   float* part_l;
   float* part_O;
+  int* cursor;  // optional [n_strips]: rotating start, see kp_flash_umma4.cu
 };
 
 __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -79,6 +81,7 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
     ptx::mbar_init(&ctl->p_full, 256);  // 128 softmax threads of each CTA (used in the leader only)
     ptx::mbar_init(&ctl->pv_done, 1);
     ptx::mbar_init(&ctl->o_done, 1);
+    if (crank == 0) ctl->start = p.cursor ? (int)((unsigned)*(volatile int*)&p.cursor[blockIdx.y] % (unsigned)ntile) : 0;
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -89,6 +92,13 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
   __syncthreads();
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
+  if (tid == 0) ctl->start_local = (int)ptx::ld_cluster_u32(ptx::mapa_u32(ptx::smem_u32(&ctl->start), 0));
+  __syncthreads();
+  const int p0 = ctl->start_local;
+  auto tile_of = [&](int t) {  // t-th tile of my walk -> tile index in the table (rotating start)
+    const int x = p0 + t;
+    return t0 + (x >= ntile ? x - ntile : x);
+  };
   const uint32_t tm = ctl->tmem_base;
   const uint32_t TM_O = tm, TM_S = tm + 256;
 
@@ -117,11 +127,11 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
         if (i < ntile)
           for (int kb = 0; kb < p.KB; ++kb) {
             load(&qh_map, &ql_map, kb * 64, qtile * 128, 16384, 2 * 32768);                         // my query tile
-            load(&eh64_map, &el64_map, kb * 64, (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the entities
+            load(&eh64_map, &el64_map, kb * 64, tile_of(i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the entities
           }
         if (i > 0)
           for (int g = 0; g < ngroup; ++g)
-            load(&eh_map, &el_map, (box0 + 2 * g + (int)crank) * 64, (t0 + i - 1) * 128, 16384, 2 * 32768);  // my 64 dims
+            load(&eh_map, &el_map, (box0 + 2 * g + (int)crank) * 64, tile_of(i - 1) * 128, 16384, 2 * 32768);  // my 64 dims
       }
     }
   } else if (warp == 1) {
@@ -161,6 +171,7 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       for (int i = 0; i < ntile; ++i) {
         const int sb = i & 1;
         const uint32_t d_s = TM_S + sb * 128;
+        if (p.cursor && chunk == 0) *(volatile int*)&p.cursor[blockIdx.y] = tile_of(i) - t0;
         for (int kb = 0; kb < p.KB; ++kb) {
           wait_slot(use);
           wait_slot(use + 1);
@@ -195,7 +206,7 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
     const int ocols = ngroup * 128;
     for (int i = 0; i < ntile; ++i) {
       const int sb = i & 1;
-      const int j0 = (t0 + i) * 128;
+      const int j0 = tile_of(i) * 128;
       ptx::mbar_wait(&ctl->s_full[sb], (i >> 1) & 1);
       ptx::tc_fence_after();
       const uint32_t s_addr = TM_S + sb * 128 + lane_off;
@@ -267,6 +278,7 @@ int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;
+  p.cursor = ctx->umma_rotate ? ctx->umma_cursor : nullptr;
   static bool configured = false;
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U2_SMEM));

@@ -17,11 +17,6 @@
 // with the same (m, l).  A thread needs the header of tile t-1 before the exponentials of tile t;
 // the chain costs one softmax latency per tile and is hidden behind S (6144 MMA cycles per own tile).
 //
-// Warp roles (320 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-5 softmax (one thread per
-// query row: own tiles S -> P in TMEM, header to the peer; foreign tiles: adopt the header), warps 6-9
-// movers (own tiles: TMEM P -> peer's shared memory, ~3000 cycles per 64 KB tile through DSMEM, off
-// the softmax chain; foreign tiles: shared memory -> TMEM B, lazy O rescale, release of the MMA warp).
-//
 // TMEM (per SM, 512 columns): O [0,256) | A [256,384): own S, overwritten by own P | B [384,512):
 // foreign P (copied in from shared memory by the row's thread; both P tiles feed TS-form MMAs).
 // MMA order of a pair (p = 0 for X, 1 for Y), mirrored by the TMA producer:
@@ -36,29 +31,21 @@
 
 namespace {
 
-constexpr int UT = 320;
+constexpr int UT = 192;
 constexpr int SLOT = 32768;
 constexpr int NSLOT = 4;
-// message buffer, 16-byte chunks, chunk-major (chunk q of row r at q*2048 + r*16):
-//   0..31 P tile (4 quarters of 8 chunks) | 32 rescale factor travelling with the tile (for the movers) |
-//   33,34 early header (m_ref, factor), slot k&1 (for the softmax threads) | 35 local staging of my own
-//   factor (softmax thread -> mover of the same row) | 36 the peer's final row sum
-constexpr int PIN_BYTES = 37 * 2048;
+constexpr int PIN_BYTES = 33 * 2048;  // 32 x 16-byte chunks per row (chunk-major: chunk q of row r at q*2048 + r*16) + header chunk
 constexpr float RESCALE_TAU = 8.0f;
 
 struct UCtl4 {
   uint64_t full[NSLOT], empty[NSLOT];
-  uint64_t s_full;                  // own S(k) complete                              (MMA commit, both CTAs of the pair)
-  uint64_t p_own, p_for;            // own / foreign P(k) complete in TMEM            (256 thread arrivals, leader only)
-  uint64_t opv_done, fpv_done;      // PV of the k-th own / foreign tile done         (MMA commit, both CTAs)
-  uint64_t a_ready[4];              // quarter q of own P(k) of this CTA's rows in A  (128 local arrivals)
-  uint64_t a_free;                  // own P(k) read back by the movers               (256 arrivals, leader only)
-  uint64_t pin_full[4];             // quarter q of message k delivered here          (128 remote arrivals)
-  uint64_t pin_empty;               // my message k consumed by the peer              (128 remote arrivals)
-  uint64_t hdr_full;                // early header k delivered here                  (128 remote arrivals)
-  uint64_t fin_full;                // the peer's final row sums delivered here       (128 remote arrivals)
+  uint64_t s_full;                  // own S(k) complete                     (MMA commit, both CTAs of the pair)
+  uint64_t p_own, p_for;            // own / foreign P(k) in TMEM            (256 thread arrivals, leader only)
+  uint64_t opv_done, fpv_done;      // PV of the k-th own / foreign tile done (MMA commit, both CTAs)
+  uint64_t pin_full, pin_empty;     // message k delivered here / my message k consumed by the peer (128 remote arrivals)
   uint64_t o_done;
   uint32_t tmem_base;
+  int start, start_local;
 };
 constexpr size_t U4_SMEM = (size_t)NSLOT * SLOT + PIN_BYTES + sizeof(UCtl4) + 1024;
 
@@ -67,6 +54,7 @@ struct UK4 {
   float* part_m;
   float* part_l;
   float* part_O;
+  int* cursor;               // optional [n_strips]: tile the running clusters of a strip are at (rotating start)
   unsigned long long* prof;  // optional [16]: MMA-thread cycles waiting on TMA slots / own P / foreign P, total
 };
 
@@ -83,20 +71,19 @@ __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, ui
 __device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
-__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
-  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
-}
 __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
 }
 
-// Own tile, first half: S row (TMEM A) -> registers, bound mask, max scan, lazy reference update.
+// Own tile: S (TMEM A) -> P, written back over S and sent to the peer CTA (pin_row = cluster address
+// of this row's first chunk in the peer's message buffer).  Same arithmetic as umma_sm::p_tile.
 template <bool SOFTMAX>
-__device__ __forceinline__ float s_row_load(uint32_t s_addr, int j0, int N, float tau, uint32_t (&r)[128], float& m_ref,
-                                            float& factor) {
+__device__ __forceinline__ void p_tile_send(uint32_t s_addr, int j0, int N, float tau, float& m_ref, float& l_run,
+                                            float& factor, uint32_t pin_row, uint64_t* pin_empty, int k) {
   using namespace umma_sm;
+  uint32_t r[128];
 #pragma unroll
   for (int q = 0; q < 4; ++q) ptx::tmem_ld_32x32(s_addr + 32 * q, reinterpret_cast<uint32_t(&)[32]>(r[32 * q]));
   ptx::tmem_ld_wait();
@@ -106,44 +93,52 @@ __device__ __forceinline__ float s_row_load(uint32_t s_addr, int j0, int N, floa
       if (j0 + c >= N) r[c] = 0xff800000u;
   }
   factor = 1.f;
-  if (!SOFTMAX) return 0.f;
-  float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  float mneg = 0.f;
+  if (SOFTMAX) {
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
 #pragma unroll
-  for (int c = 0; c < 128; c += 4) {
+    for (int c = 0; c < 128; c += 4) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(r[c + u]));
+      for (int u = 0; u < 4; ++u) mx[u] = fmaxf(mx[u], __uint_as_float(r[c + u]));
+    }
+    const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
+    if (m_ref == -INFINITY) {
+      m_ref = m;
+    } else if (m > m_ref + tau) {
+      factor = ex2((m_ref - m) * LOG2E);
+      m_ref = m;
+    }
+    mneg = (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
   }
-  const float m = fmaxf(fmaxf(mx[0], mx[1]), fmaxf(mx[2], mx[3]));
-  if (m_ref == -INFINITY) {
-    m_ref = m;
-  } else if (m > m_ref + tau) {
-    factor = ex2((m_ref - m) * LOG2E);
-    m_ref = m;
-  }
-  return (m_ref == -INFINITY) ? 0.f : m_ref * LOG2E;
-}
-// Own tile, second half: 32 logits -> probabilities, bf16 hi / lo packed (same arithmetic as umma_sm::p_tile).
-template <bool SOFTMAX>
-__device__ __forceinline__ float p_chunk(const uint32_t* r, float mneg, uint32_t (&w)[32]) {
-  using namespace umma_sm;
+  // the peer has consumed my previous message (normally long ago: it gates the peer's own next tile)
+  if (k > 0) ptx::mbar_wait_cluster(pin_empty, (k - 1) & 1);
   float sum0 = 0.f, sum1 = 0.f;
 #pragma unroll
-  for (int c = 0; c < 32; c += 2) {
-    float p0, p1;
-    if (SOFTMAX) {
-      p0 = ex2(__fmaf_rn(__uint_as_float(r[c]), LOG2E, -mneg));
-      p1 = ex2(__fmaf_rn(__uint_as_float(r[c + 1]), LOG2E, -mneg));
-    } else {
-      p0 = rcp(1.f + ex2(-LOG2E * __uint_as_float(r[c])));
-      p1 = rcp(1.f + ex2(-LOG2E * __uint_as_float(r[c + 1])));
+  for (int q = 0; q < 4; ++q) {
+    uint32_t w[32];
+#pragma unroll
+    for (int c = 0; c < 32; c += 2) {
+      float p0, p1;
+      if (SOFTMAX) {
+        p0 = ex2(__fmaf_rn(__uint_as_float(r[32 * q + c]), LOG2E, -mneg));
+        p1 = ex2(__fmaf_rn(__uint_as_float(r[32 * q + c + 1]), LOG2E, -mneg));
+      } else {
+        p0 = rcp(1.f + ex2(-LOG2E * __uint_as_float(r[32 * q + c])));
+        p1 = rcp(1.f + ex2(-LOG2E * __uint_as_float(r[32 * q + c + 1])));
+      }
+      sum0 += p0;
+      sum1 += p1;
+      const uint32_t hi = bf16x2(p0, p1);
+      w[c >> 1] = hi;
+      w[16 + (c >> 1)] = bf16x2(p0 - __uint_as_float(hi << 16), p1 - __uint_as_float(hi & 0xffff0000u));
     }
-    sum0 += p0;
-    sum1 += p1;
-    const uint32_t hi = bf16x2(p0, p1);
-    w[c >> 1] = hi;
-    w[16 + (c >> 1)] = bf16x2(p0 - __uint_as_float(hi << 16), p1 - __uint_as_float(hi & 0xffff0000u));
+    ptx::tmem_st_32x32(s_addr + 32 * q, w);
+#pragma unroll
+    for (int v = 0; v < 8; ++v) st_cluster_v4(pin_row + (uint32_t)(8 * q + v) * 2048u, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
   }
-  return sum0 + sum1;
+  const float sum = sum0 + sum1;
+  st_cluster_v4(pin_row + 32u * 2048u, __float_as_uint(m_ref), __float_as_uint(factor), __float_as_uint(sum), 0u);
+  l_run = l_run * factor + sum;
 }
 
 __global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(UT, 1)
@@ -171,29 +166,25 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
   const int ngroup = p.groups_per_chunk;
   const int box0 = chunk * ngroup * 2;
   const uint16_t pair_mask = (uint16_t)(3u << lead);
-  const bool softmax = (p.mode & 15) == KP_FLASH_SOFTMAX;
-  const bool dry = (p.mode & 16) != 0;     // timing experiments: TMA + MMA pipeline only (results are garbage)
-  const bool noload = (p.mode & 32) != 0;  // ... and without the TMA traffic
 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
       ptx::mbar_init(&ctl->empty[s], 1);
     }
-    for (int q = 0; q < 4; ++q) {
-      ptx::mbar_init(&ctl->a_ready[q], 128);
-      ptx::mbar_init(&ctl->pin_full[q], 128);
-    }
     ptx::mbar_init(&ctl->s_full, 1);
     ptx::mbar_init(&ctl->p_own, 256);
     ptx::mbar_init(&ctl->p_for, 256);
     ptx::mbar_init(&ctl->opv_done, 1);
     ptx::mbar_init(&ctl->fpv_done, 1);
+    ptx::mbar_init(&ctl->pin_full, 128);
     ptx::mbar_init(&ctl->pin_empty, 128);
-    ptx::mbar_init(&ctl->hdr_full, 128);
-    ptx::mbar_init(&ctl->fin_full, 128);
-    ptx::mbar_init(&ctl->a_free, 256);
     ptx::mbar_init(&ctl->o_done, 1);
+    // Rotating start: a cluster that begins while others are mid-table joins them at the tile they are
+    // at and wraps around (the online softmax is order-independent), so the resident clusters walk
+    // the table together and every entity tile is fetched from HBM once per wave instead of once per
+    // cluster (ncu at 4096 candidates: 508 GB of DRAM reads per launch without it).
+    if (crank == 0) ctl->start = p.cursor ? (int)((unsigned)*(volatile int*)&p.cursor[blockIdx.y] % (unsigned)ntile) : 0;
     ptx::fence_barrier_init();
   }
   if (warp == 1) {
@@ -204,12 +195,19 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
   __syncthreads();
   ptx::cluster_sync_all();
   ptx::tc_fence_after();
+  if (tid == 0) ctl->start_local = (int)ptx::ld_cluster_u32(ptx::mapa_u32(ptx::smem_u32(&ctl->start), 0));
+  __syncthreads();
+  const int p0 = ctl->start_local;
+  auto tile_of = [&](int t) {  // t-th tile of my walk -> tile index in the table
+    const int x = p0 + t;
+    return t0 + (x >= ntile ? x - ntile : x);
+  };
   const uint32_t tm = ctl->tmem_base;
   const uint32_t TM_O = tm, TM_A = tm + 256, TM_B = tm + 384;
 
   if (warp == 0) {
     // ------------------------------- TMA producer (every CTA) -------------------------------
-    if (lane == 0 && !noload) {
+    if (lane == 0) {
       ptx::prefetch_tmap(&eh_map);
       ptx::prefetch_tmap(&el_map);
       ptx::prefetch_tmap(&eh64_map);
@@ -230,12 +228,12 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       auto load_s = [&](int t) {
         for (int kb = 0; kb < p.KB; ++kb) {
           load(&qh_map, &ql_map, kb * 64, qtile * 128, 16384, 2 * 32768);
-          load(&eh64_map, &el64_map, kb * 64, (t0 + t) * 128 + (int)half * 64, 8192, 2 * 16384);
+          load(&eh64_map, &el64_map, kb * 64, tile_of(t) * 128 + (int)half * 64, 8192, 2 * 16384);
         }
       };
       auto load_pv = [&](int t) {
         for (int g = 0; g < ngroup; ++g)
-          load(&eh_map, &el_map, (box0 + 2 * g + (int)half) * 64, (t0 + t) * 128, 16384, 2 * 32768);
+          load(&eh_map, &el_map, (box0 + 2 * g + (int)half) * 64, tile_of(t) * 128, 16384, 2 * 32768);
       };
       if (par == 0) load_s(0);
       for (int t = 0; t < ntile; ++t) {
@@ -254,23 +252,14 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       long long w_slot = 0, w_own = 0, w_for = 0;
       const long long t_begin = clock64();
       auto wait_slot = [&](uint32_t u) {
-        if (noload) return;
         if (ptx::mbar_try_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1)) return;
         const long long a = clock64();
         ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1);
         w_slot += clock64() - a;
       };
-      auto release = [&](uint32_t u) {
-        if (!noload) ptx::umma2_commit_mc(&ctl->empty[u % NSLOT], pair_mask);
-      };
+      auto release = [&](uint32_t u) { ptx::umma2_commit_mc(&ctl->empty[u % NSLOT], pair_mask); };
       auto mma_s = [&](int t) {
-        const int k = t >> 1;
-        if (k > 0 && !dry) {  // the movers have read P(k-1) out of A (PV(k-1) itself precedes S(k) in issue order)
-          const long long a = clock64();
-          ptx::mbar_wait_cluster(&ctl->a_free, (k - 1) & 1);
-          w_own += clock64() - a;
-          ptx::tc_fence_after();
-        }
+        if (p.cursor && crank == 0) *(volatile int*)&p.cursor[blockIdx.y] = tile_of(t) - t0;
         for (int kb = 0; kb < p.KB; ++kb) {
           wait_slot(use);
           wait_slot(use + 1);
@@ -280,7 +269,6 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
-            if (p.mode & 64) break;  // timing experiment: no S MMAs
             ptx::umma2_bf16(TM_A, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
             ptx::umma2_bf16(TM_A, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
             ptx::umma2_bf16(TM_A, al + kk * 2, bh + kk * 2, idesc_s, 1u);
@@ -294,40 +282,13 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       auto mma_pv = [&](int t) {
         const bool own = (t & 1) == par;
         const int k = t >> 1;
-        if (!dry) {
+        {
           const long long a = clock64();
           ptx::mbar_wait_cluster(own ? &ctl->p_own : &ctl->p_for, k & 1);
           (own ? w_own : w_for) += clock64() - a;
         }
         ptx::tc_fence_after();
         const uint32_t p_t = own ? TM_A : TM_B;
-        if (ngroup == 2) {
-          // both 128-dim groups at once, alternating accumulators: back-to-back MMAs into the SAME
-          // accumulator serialise on the accumulate latency (measured ~105 cycles per M256 N128 K16
-          // instead of ~80 when two independent chains alternate)
-          wait_slot(use);
-          wait_slot(use + 1);
-          ptx::tc_fence_after();
-          const uint32_t e0 = ring_a + (use % NSLOT) * SLOT, e1 = ring_a + ((use + 1) % NSLOT) * SLOT;
-          const uint64_t b0h = DMN + (e0 >> 4), b0l = DMN + ((e0 + 16384) >> 4);
-          const uint64_t b1h = DMN + (e1 >> 4), b1l = DMN + ((e1 + 16384) >> 4);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks) {
-            if (p.mode & 128) break;  // timing experiment: no PV MMAs
-            const uint32_t a_hi = p_t + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
-            const uint32_t acc = (t > 0 || ks > 0) ? 1u : 0u;
-            const uint64_t o = ks * (2048 >> 4);
-            ptx::umma2_bf16_ts(TM_O, a_hi, b0h + o, idesc_pv, acc);
-            ptx::umma2_bf16_ts(TM_O + 128, a_hi, b1h + o, idesc_pv, acc);
-            ptx::umma2_bf16_ts(TM_O, a_hi, b0l + o, idesc_pv, 1u);
-            ptx::umma2_bf16_ts(TM_O + 128, a_hi, b1l + o, idesc_pv, 1u);
-            ptx::umma2_bf16_ts(TM_O, a_lo, b0h + o, idesc_pv, 1u);
-            ptx::umma2_bf16_ts(TM_O + 128, a_lo, b1h + o, idesc_pv, 1u);
-          }
-          release(use);
-          release(use + 1);
-          use += 2;
-        } else
         for (int g = 0; g < ngroup; ++g) {
           wait_slot(use);
           ptx::tc_fence_after();
@@ -360,178 +321,75 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
         atomicAdd(p.prof + 3, (unsigned long long)(clock64() - t_begin));
       }
     }
-  } else if (dry) {
-    // timing experiment: no softmax, no exchange
-  } else if (warp >= 6) {
-    // ------------------------------- movers (every CTA, own rows) -------------------------------
-    const int sub = warp & 3;
-    const int row = sub * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
-    const uint32_t p_for_lead = ptx::mapa_u32(ptx::smem_u32(&ctl->p_for), lead);
-    const uint32_t a_free_lead = ptx::mapa_u32(ptx::smem_u32(&ctl->a_free), lead);
-    const uint32_t pin_local = ptx::smem_u32(pin) + (uint32_t)row * 16u;
-    const uint32_t pin_peer = ptx::mapa_u32(pin_local, peer);
-    const uint32_t pin_full_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_full[0]), peer);
-    const uint32_t pin_empty_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_empty), peer);
-    const int ocols = ngroup * 128;
-    long long c_send = 0, c_wpin = 0;
-    for (int t = 0; t < ntile; ++t) {
-      const bool own = (t & 1) == par;
-      const int k = t >> 1;
-      if (own) {
-        // ship P(k) quarter by quarter as the softmax threads produce it: TMEM A -> registers -> peer's buffer
-        long long c0 = 0;
-        uint32_t fac = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          ptx::mbar_wait(&ctl->a_ready[q], k & 1);
-          ptx::tc_fence_after();
-          uint32_t w[32];
-          ptx::tmem_ld_32x32(TM_A + lane_off + 32 * q, w);
-          ptx::tmem_ld_wait();
-          if (q == 0) {
-            c0 = clock64();
-            fac = ld_shared_v4(pin_local + 35u * 2048u).x;  // this tile's rescale factor, staged by my row's softmax thread
-            if (k > 0) ptx::mbar_wait_cluster(&ctl->pin_empty, (k - 1) & 1);
-          }
-          if (q == 3) {
-            ptx::tc_fence_before();
-            ptx::mbar_arrive_cluster(a_free_lead);  // A may be overwritten by S(k+1)
-            st_cluster_v4(pin_peer + 32u * 2048u, fac, 0u, 0u, 0u);
-          }
-#pragma unroll
-          for (int v = 0; v < 8; ++v)
-            st_cluster_v4(pin_peer + (uint32_t)(8 * q + v) * 2048u, w[4 * v], w[4 * v + 1], w[4 * v + 2], w[4 * v + 3]);
-          ptx::mbar_arrive_cluster(pin_full_peer + 8u * q);  // release: quarter q of my row is complete
-        }
-        c_send += clock64() - c0;
-      } else {
-        // foreign P(k): message buffer -> TMEM B, then the tile's lazy rescale of O, then PV(t) may start
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const long long c0 = clock64();
-          ptx::mbar_wait_cluster(&ctl->pin_full[q], k & 1);
-          c_wpin += clock64() - c0;
-          if (q == 0 && k > 0) {  // B still feeds PV of the previous foreign tile
-            ptx::mbar_wait(&ctl->fpv_done, (k - 1) & 1);
-            ptx::tc_fence_after();
-          }
-          uint32_t w[32];
-#pragma unroll
-          for (int v = 0; v < 8; ++v) {
-            const uint4 x = ld_shared_v4(pin_local + (uint32_t)(8 * q + v) * 2048u);
-            w[4 * v] = x.x;
-            w[4 * v + 1] = x.y;
-            w[4 * v + 2] = x.z;
-            w[4 * v + 3] = x.w;
-          }
-          ptx::tmem_st_32x32(TM_B + lane_off + 32 * q, w);
-        }
-        const float factor = __uint_as_float(ld_shared_v4(pin_local + 32u * 2048u).x);
-        ptx::mbar_arrive_cluster(pin_empty_peer);  // release: the buffer may be overwritten
-        if (__any_sync(0xffffffffu, factor != 1.f)) {
-          // O holds tiles < t only once PV(t-1) (an own tile) has completed; t >= 1 here
-          ptx::mbar_wait(&ctl->opv_done, ((t - 1) >> 1) & 1);
-          ptx::tc_fence_after();
-#pragma unroll 1
-          for (int c0 = 0; c0 < ocols; c0 += 32) {
-            uint32_t r[32];
-            ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
-            ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
-          }
-        }
-        ptx::tmem_st_wait();
-        ptx::tc_fence_before();
-        ptx::mbar_arrive_cluster(p_for_lead);
-      }
-    }
-    if (p.prof && tid == 6 * 32 && leader) {
-      atomicAdd(p.prof + 4, (unsigned long long)c_send);
-      atomicAdd(p.prof + 5, (unsigned long long)c_wpin);
-    }
   } else {
-    // ------------------------------- softmax / epilogue (every CTA, own rows) -------------------------------
+    // ------------------------------- softmax / exchange / epilogue (every CTA, own rows) -------------------------------
     const int sub = warp & 3;
     const int row = sub * 32 + lane;
     const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
     const int g = qtile * 128 + row;
     const uint32_t p_own_lead = ptx::mapa_u32(ptx::smem_u32(&ctl->p_own), lead);
+    const uint32_t p_for_lead = ptx::mapa_u32(ptx::smem_u32(&ctl->p_for), lead);
     const uint32_t pin_local = ptx::smem_u32(pin) + (uint32_t)row * 16u;
     const uint32_t pin_peer = ptx::mapa_u32(pin_local, peer);
-    const uint32_t hdr_full_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->hdr_full), peer);
-    // m_ref: reference max after the tiles folded so far (both pairs agree on it tile by tile);
-    // l_mine: sum of MY tiles' probabilities, rescaled by every later factor (own or foreign)
-    float m_ref = -INFINITY, l_mine = 0.f;
+    const uint32_t pin_full_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_full), peer);
+    const uint32_t pin_empty_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_empty), peer);
+    float m_ref = -INFINITY, l_run = 0.f;
     const int ocols = ngroup * 128;
-    long long c_whdr = 0, c_wsf = 0, c_soft = 0;
     for (int t = 0; t < ntile; ++t) {
       const bool own = (t & 1) == par;
       const int k = t >> 1;
+      float factor;
       if (own) {
-        const long long c0 = clock64();
         ptx::mbar_wait(&ctl->s_full, k & 1);
-        const long long c1 = clock64();
-        c_wsf += c1 - c0;
         ptx::tc_fence_after();
-        const int j0 = (t0 + t) * 128;
-        uint32_t r[128];
-        float factor;
-        const float mneg = softmax ? s_row_load<true>(TM_A + lane_off, j0, p.N, RESCALE_TAU, r, m_ref, factor)
-                                   : s_row_load<false>(TM_A + lane_off, j0, p.N, RESCALE_TAU, r, m_ref, factor);
-        // early header: the peer's softmax of tile t+1 only needs (m_ref, factor).  Slot k&1: the
-        // peer's thread has read header k-2 (it gated the peer's tile between, whose header gated this one)
-        st_cluster_v4(pin_peer + (uint32_t)(33 + (k & 1)) * 2048u, __float_as_uint(m_ref), __float_as_uint(factor), 0u, 0u);
-        ptx::mbar_arrive_cluster(hdr_full_peer);
-        st_shared_v4(pin_local + 35u * 2048u, __float_as_uint(factor), 0u, 0u, 0u);  // for my row's mover
-        if (__any_sync(0xffffffffu, factor != 1.f)) {
-          // O holds tiles < t only once PV(t-1) (a foreign tile) has completed; t >= 1 here
-          ptx::mbar_wait(&ctl->fpv_done, ((t - 1) >> 1) & 1);
-          ptx::tc_fence_after();
-#pragma unroll 1
-          for (int c0 = 0; c0 < ocols; c0 += 32) {
-            uint32_t o[32];
-            ptx::tmem_ld_32x32(TM_O + lane_off + c0, o);
-            ptx::tmem_ld_wait();
-#pragma unroll
-            for (int c = 0; c < 32; ++c) o[c] = __float_as_uint(__uint_as_float(o[c]) * factor);
-            ptx::tmem_st_32x32(TM_O + lane_off + c0, o);
-          }
-        }
-        float sum = 0.f;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          uint32_t w[32];
-          sum += softmax ? p_chunk<true>(&r[32 * q], mneg, w) : p_chunk<false>(&r[32 * q], mneg, w);
-          ptx::tmem_st_32x32(TM_A + lane_off + 32 * q, w);
-          ptx::tmem_st_wait();
-          ptx::tc_fence_before();
-          ptx::mbar_arrive(&ctl->a_ready[q]);  // movers of this CTA: quarter q of P(k) is in A
-        }
-        l_mine = l_mine * factor + sum;
-        ptx::mbar_arrive_cluster(p_own_lead);  // PV(t) may start
-        c_soft += clock64() - c1;
+        const int j0 = tile_of(t) * 128;
+        if (p.mode == KP_FLASH_SOFTMAX)
+          p_tile_send<true>(TM_A + lane_off, j0, p.N, RESCALE_TAU, m_ref, l_run, factor, pin_peer, &ctl->pin_empty, k);
+        else
+          p_tile_send<false>(TM_A + lane_off, j0, p.N, RESCALE_TAU, m_ref, l_run, factor, pin_peer, &ctl->pin_empty, k);
+        ptx::mbar_arrive_cluster(pin_full_peer);  // release: my row of the message is complete
       } else {
-        const long long c0 = clock64();
-        ptx::mbar_wait_cluster(&ctl->hdr_full, k & 1);
-        c_whdr += clock64() - c0;
-        const uint4 h = ld_shared_v4(pin_local + (uint32_t)(33 + (k & 1)) * 2048u);
+        ptx::mbar_wait_cluster(&ctl->pin_full, k & 1);
+        uint32_t w[128];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+          const uint4 v = ld_shared_v4(pin_local + (uint32_t)q * 2048u);
+          w[4 * q] = v.x;
+          w[4 * q + 1] = v.y;
+          w[4 * q + 2] = v.z;
+          w[4 * q + 3] = v.w;
+        }
+        const uint4 h = ld_shared_v4(pin_local + 32u * 2048u);
+        ptx::mbar_arrive_cluster(pin_empty_peer);  // release: the buffer may be overwritten
         m_ref = __uint_as_float(h.x);
-        l_mine *= __uint_as_float(h.y);
+        factor = __uint_as_float(h.y);
+        l_run = l_run * factor + __uint_as_float(h.z);
+        if (k > 0) {  // B still feeds PV of the previous foreign tile
+          ptx::mbar_wait(&ctl->fpv_done, (k - 1) & 1);
+          ptx::tc_fence_after();
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q) ptx::tmem_st_32x32(TM_B + lane_off + 32 * q, reinterpret_cast<uint32_t(&)[32]>(w[32 * q]));
       }
+      if (__any_sync(0xffffffffu, factor != 1.f)) {
+        // O holds tiles < t only once PV(t-1) has completed (t >= 1 here: the first tile never rescales)
+        const bool prev_own = ((t - 1) & 1) == par;
+        ptx::mbar_wait(prev_own ? &ctl->opv_done : &ctl->fpv_done, ((t - 1) >> 1) & 1);
+        ptx::tc_fence_after();
+#pragma unroll 1
+        for (int c0 = 0; c0 < ocols; c0 += 32) {
+          uint32_t r[32];
+          ptx::tmem_ld_32x32(TM_O + lane_off + c0, r);
+          ptx::tmem_ld_wait();
+#pragma unroll
+          for (int c = 0; c < 32; ++c) r[c] = __float_as_uint(__uint_as_float(r[c]) * factor);
+          ptx::tmem_st_32x32(TM_O + lane_off + c0, r);
+        }
+      }
+      ptx::tmem_st_wait();
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster(own ? p_own_lead : p_for_lead);
     }
-    if (p.prof && tid == 2 * 32 && leader) {
-      atomicAdd(p.prof + 6, (unsigned long long)c_whdr);
-      atomicAdd(p.prof + 7, (unsigned long long)c_wsf);
-      atomicAdd(p.prof + 8, (unsigned long long)c_soft);
-    }
-    // l = my tiles' share + the peer's
-    st_cluster_v4(pin_peer + 36u * 2048u, __float_as_uint(l_mine), 0u, 0u, 0u);
-    ptx::mbar_arrive_cluster(ptx::mapa_u32(ptx::smem_u32(&ctl->fin_full), peer));
-    ptx::mbar_wait_cluster(&ctl->fin_full, 0);
-    const float l_run = l_mine + __uint_as_float(ld_shared_v4(pin_local + 36u * 2048u).x);
     ptx::mbar_wait(&ctl->o_done, 0);
     ptx::tc_fence_after();
     const size_t slot = (size_t)strip * p.G + (g < p.G ? g : 0);
@@ -605,6 +463,7 @@ int kp_flash_umma4_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   p.part_l = part_l;
   p.part_O = part_O;
   p.prof = ctx->umma_prof;
+  p.cursor = ctx->umma_rotate ? ctx->umma_cursor : nullptr;
   static bool configured = false;
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U4_SMEM));

@@ -57,6 +57,8 @@ struct kp_ctx {
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
   int64_t umma_x4 = 1;   // rows wider than 256 floats: clusters of two pairs that compute S once (kp_flash_umma4.cu)
+  int64_t umma_rotate = 1;  // rotating start of the entity walk (clusters share the table pass through L2)
+  int* umma_cursor = nullptr;  // device [64]
   unsigned long long* umma_prof = nullptr;  // device [4], option "umma_prof" = 1: wait-cycle counters of the cluster-4 pass
   int64_t umma_cq = 0;  // query tiles per cluster of the tcgen05 pass (0 = automatic)
 
