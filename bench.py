@@ -344,6 +344,11 @@ def main():
             peak, unit, src = peaks.get("hbm_gbs", 6650.0), "GB/s", "hbm_gbs"
             achieved = work["units"] / (dom_ms / dom_n * 1e-3) / 1e9 if dom_n else None
         src += " of measured (MEASURED_PEAKS.json)" if peaks else " of fallback"
+        traffic = None  # DRAM bytes per launch of the dominant kernel: from the committed ncu capture of this exact size
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))[f"{args.workload}/{C}"]["dram_bytes_per_launch"]
+        except Exception:
+            pass
         line = {
             "metric": "candidate explanations evaluated/sec (post-train + filtered rank)",
             "value": total / (t_kernel * 1e-3), "unit": "candidates/s", "n_gpus": world, "steps": args.steps,
@@ -359,7 +364,7 @@ def main():
                     "d2h_bytes_per_step": int(out.numel() * 4), "ms_per_step": t_e2e / args.steps},
             "gpu_launches": int(launches),
             "roofline": {"bound": work["bound"], "kernel": work["what"], "achieved": achieved, "peak": peak, "unit": unit,
-                         "frac": (achieved / peak) if achieved else None, "traffic": None, "peak_source": src,
+                         "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": src,
                          "launches_timed": int(dom_n), "avg_launch_ms": (dom_ms / dom_n) if dom_n else None,
                          "share_of_step": dom_ms / t_kernel if t_kernel else None},
             "clocks": sampler.summary(w0, w1) if sampler else None,
