@@ -36,6 +36,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_x4 = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_rank")) {
+    ctx->umma_rank = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "umma_rotate")) {
     ctx->umma_rotate = value;
     return KP_OK;
@@ -94,6 +98,10 @@ extern "C" int kp_stat(kp_ctx* ctx, const char* name, double* out) {
   for (int i = 0; i < kp_ctx::T_NCAT; ++i) {
     if (!strncmp(name, "ms_", 3) && !strcmp(name + 3, cats[i])) { *out = ctx->t_ms[i]; return KP_OK; }
     if (!strncmp(name, "n_", 2) && !strcmp(name + 2, cats[i])) { *out = (double)ctx->t_n[i]; return KP_OK; }
+  }
+  if (!strcmp(name, "rank_rechecks")) {
+    *out = (double)ctx->rank_rechecks;
+    return KP_OK;
   }
   if (!strncmp(name, "umma_prof_", 10) && ctx->umma_prof) {  // slot / own / for / total (MMA-thread cycles, summed over pairs)
     static const char* w[] = {"slot", "own", "for", "total", "send", "wpin", "whdr", "wsfull", "soft"};

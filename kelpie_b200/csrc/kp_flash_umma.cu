@@ -381,44 +381,81 @@ int kp_flash_umma_plan(kp_ctx* ctx, int G, int* n_strips) {
   return u.bpc;
 }
 
+namespace {
+// L2 norm of every entity row (used by the tcgen05 rank pass for its per-pair error margin)
+__global__ void row_norm_kernel(const float* __restrict__ src, long long rows, int D, long long rows_pad, float* __restrict__ out) {
+  const long long r = blockIdx.x * (long long)(blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (r >= rows_pad) return;
+  float a = 0.f;
+  if (r < rows)
+    for (int k = lane; k < D; k += 32) a = __fmaf_rn(src[r * D + k], src[r * D + k], a);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+  if (lane == 0) out[r] = sqrtf(a);
+}
+}  // namespace
+
+// Split bf16 entity tables, their TMA maps, the row norms and the walk cursors (once per context).
+int kp_umma_tables(kp_ctx* ctx, cudaStream_t st) {
+  if (ctx->um.ready) return KP_OK;
+  const UPlan u = umma_plan(ctx, 128);
+  const int D = ctx->D, Dpad = u.Dpad;
+  int rc;
+  const long long Npad = ((ctx->N + 127) / 128) * 128;
+  void *h = nullptr, *l = nullptr, *nrm = nullptr;
+  if (cudaMalloc(&h, (size_t)Npad * Dpad * 2) != cudaSuccess || cudaMalloc(&l, (size_t)Npad * Dpad * 2) != cudaSuccess ||
+      cudaMalloc(&nrm, (size_t)Npad * 4) != cudaSuccess)
+    KP_FAIL(ctx, KP_ENOMEM, "cannot allocate the split bf16 entity tables (%lld x %d)", Npad, Dpad);
+  ctx->owned.push_back(h);
+  ctx->owned.push_back(l);
+  ctx->owned.push_back(nrm);
+  split_bf16_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->ent, ctx->N, D, Npad, Dpad, (__nv_bfloat16*)h, (__nv_bfloat16*)l);
+  KP_LAUNCHED(ctx, 1);
+  row_norm_kernel<<<(unsigned)((Npad + 7) / 8), 256, 0, st>>>(ctx->ent, ctx->N, D, Npad, (float*)nrm);
+  KP_LAUNCHED(ctx, 1);
+  if ((rc = encode_bf16(ctx, &ctx->um.eh_map, h, Npad, Dpad)) != KP_OK) return rc;
+  if ((rc = encode_bf16(ctx, &ctx->um.el_map, l, Npad, Dpad)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &ctx->um.eh64_map, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &ctx->um.el64_map, l, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
+  ctx->um.ent_hi = h;
+  ctx->um.ent_lo = l;
+  ctx->um.enorm = (float*)nrm;
+  ctx->um.Dpad = Dpad;
+  void* cur = nullptr;
+  if (cudaMalloc(&cur, 64 * sizeof(int)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "cannot allocate the walk cursors");
+  ctx->owned.push_back(cur);
+  KP_CUDA(ctx, cudaMemsetAsync(cur, 0, 64 * sizeof(int), st));
+  ctx->umma_cursor = static_cast<int*>(cur);
+  ctx->um.ready = true;
+  return KP_OK;
+}
+
+// fp32 [G, D] rows -> bf16 hi / lo [Gpad, Dpad] in workspace arena 1 + their TMA maps (box {64, 128}).
+int kp_umma_split_rows(kp_ctx* ctx, const float* mat, int G, long long Gpad, CUtensorMap* hi_map, CUtensorMap* lo_map,
+                       cudaStream_t st) {
+  const int Dpad = ctx->um.Dpad;
+  const size_t qbytes = (size_t)Gpad * Dpad * 2;
+  int rc;
+  if ((rc = kp_ws_reserve(ctx, 2 * qbytes + 2048, 1)) != KP_OK) return rc;
+  __nv_bfloat16* qh = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1]);
+  __nv_bfloat16* ql = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1] + ((qbytes + 1023) & ~size_t(1023)));
+  split_bf16_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(mat, G, ctx->D, Gpad, Dpad, qh, ql);
+  KP_LAUNCHED(ctx, 1);
+  if ((rc = encode_bf16(ctx, hi_map, qh, Gpad, Dpad)) != KP_OK) return rc;
+  if ((rc = encode_bf16(ctx, lo_map, ql, Gpad, Dpad)) != KP_OK) return rc;
+  return KP_OK;
+}
+
 int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m, float* part_l, float* part_O,
                   cudaStream_t st) {
   if (G <= 0) return KP_OK;
   const UPlan u = umma_plan(ctx, G);
-  const int D = ctx->D, Dpad = u.Dpad;
+  const int D = ctx->D;
   int rc;
-  if (!ctx->um.ready) {
-    const long long Npad = ((ctx->N + 127) / 128) * 128;
-    void *h = nullptr, *l = nullptr;
-    if (cudaMalloc(&h, (size_t)Npad * Dpad * 2) != cudaSuccess || cudaMalloc(&l, (size_t)Npad * Dpad * 2) != cudaSuccess)
-      KP_FAIL(ctx, KP_ENOMEM, "cannot allocate the split bf16 entity tables (%lld x %d)", Npad, Dpad);
-    ctx->owned.push_back(h);
-    ctx->owned.push_back(l);
-    split_bf16_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(ctx->ent, ctx->N, D, Npad, Dpad, (__nv_bfloat16*)h, (__nv_bfloat16*)l);
-    KP_LAUNCHED(ctx, 1);
-    if ((rc = encode_bf16(ctx, &ctx->um.eh_map, h, Npad, Dpad)) != KP_OK) return rc;
-    if ((rc = encode_bf16(ctx, &ctx->um.el_map, l, Npad, Dpad)) != KP_OK) return rc;
-    if ((rc = kp_encode_2d(ctx, &ctx->um.eh64_map, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
-    if ((rc = kp_encode_2d(ctx, &ctx->um.el64_map, l, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Dpad, Dpad, 64, 64, true)) != KP_OK) return rc;
-    ctx->um.ent_hi = h;
-    ctx->um.ent_lo = l;
-    void* cur = nullptr;
-    if (cudaMalloc(&cur, 64 * sizeof(int)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "cannot allocate the walk cursors");
-    ctx->owned.push_back(cur);
-    KP_CUDA(ctx, cudaMemsetAsync(cur, 0, 64 * sizeof(int), st));
-    ctx->umma_cursor = static_cast<int*>(cur);
-    ctx->um.ready = true;
-  }
-  const long long Gpad = (long long)u.n_qt * 128;
-  const size_t qbytes = (size_t)Gpad * Dpad * 2;
-  if ((rc = kp_ws_reserve(ctx, 2 * qbytes + 2048, 1)) != KP_OK) return rc;
-  __nv_bfloat16* qh = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1]);
-  __nv_bfloat16* ql = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1] + ((qbytes + 1023) & ~size_t(1023)));
-  split_bf16_kernel<<<ctx->sm_count * 4, 256, 0, st>>>(qmat, G, D, Gpad, Dpad, qh, ql);
-  KP_LAUNCHED(ctx, 1);
+  if ((rc = kp_umma_tables(ctx, st)) != KP_OK) return rc;
   CUtensorMap qh_map, ql_map;
-  if ((rc = encode_bf16(ctx, &qh_map, qh, Gpad, Dpad)) != KP_OK) return rc;
-  if ((rc = encode_bf16(ctx, &ql_map, ql, Gpad, Dpad)) != KP_OK) return rc;
+  if ((rc = kp_umma_split_rows(ctx, qmat, G, (long long)u.n_qt * 128, &qh_map, &ql_map, st)) != KP_OK) return rc;
 
   if (u.quad)
     return kp_flash_umma4_launch(ctx, qh_map, ql_map, G, u.KBs, u.bpc / 2, u.n_qt, u.n_strips, u.tps, mode, part_m, part_l,

@@ -43,6 +43,8 @@ struct kp_ctx {
     void *ent_hi = nullptr, *ent_lo = nullptr;
     CUtensorMap eh_map, el_map;      // box {64 bf16, 128 rows}
     CUtensorMap eh64_map, el64_map;  // box {64 bf16, 64 rows} (half entity tile, cta_group::2 pass)
+    float* enorm = nullptr;          // [Npad] L2 norm of every entity row
+    int Dpad = 0;                    // padded row width of the split tables
   } um;
 
   // grow-only device workspace arenas (0: drivers' scratch, 1: the tcgen05 pass's own scratch)
@@ -53,10 +55,12 @@ struct kp_ctx {
   size_t ws_arena_bytes[2] = {0, 0};
 
   int64_t launches = 0;
+  int64_t rank_rechecks = 0;  // pairs the tensor-core rank pass handed to the exact re-check so far
   int64_t force_simt = 0;
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
   int64_t umma_x4 = 1;   // rows wider than 256 floats: clusters of two pairs that compute S once (kp_flash_umma4.cu)
+  int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
   int64_t umma_rotate = 1;  // rotating start of the entity walk (clusters share the table pass through L2)
   int* umma_cursor = nullptr;  // device [64]
   unsigned long long* umma_prof = nullptr;  // device [4], option "umma_prof" = 1: wait-cycle counters of the cluster-4 pass
@@ -190,3 +194,9 @@ int kp_flash_umma4_sms(kp_ctx* ctx);
 int kp_flash_umma4_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
                           int groups_per_chunk, int n_qt, int n_strips, int tps, int mode, float* part_m, float* part_l,
                           float* part_O, cudaStream_t st);
+int kp_umma_tables(kp_ctx* ctx, cudaStream_t st);
+int kp_umma_split_rows(kp_ctx* ctx, const float* mat, int G, long long Gpad, CUtensorMap* hi_map, CUtensorMap* lo_map,
+                       cudaStream_t st);
+// kp_rank_umma.cu: RANK epilogue of the DOT pass on the tensor cores; same counters as kp_pass_launch (bit-identical)
+bool kp_rank_umma_usable(kp_ctx* ctx, const kp_pass_args& a);
+int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st);

@@ -271,7 +271,11 @@ int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic
   a.flt_ids = ids;
   a.cnt = cnt;
   a.best = best;
-  if ((rc = (kp_stream_usable(ctx, Q) ? kp_stream_launch(ctx, a, st) : kp_pass_launch(ctx, a, st))) != KP_OK) return rc;
+  if (kp_rank_umma_usable(ctx, a))
+    rc = kp_rank_umma_launch(ctx, a, st);
+  else
+    rc = kp_stream_usable(ctx, Q) ? kp_stream_launch(ctx, a, st) : kp_pass_launch(ctx, a, st);
+  if (rc != KP_OK) return rc;
   finalize_ranks<<<(Q + 255) / 256, 256, 0, st>>>(Q, N, mode, minimize ? 1 : 0, mimic ? 1 : 0, cnt, best, target, self,
                                                  tgt_ent, fbeg, fend, ids, target_score, best_score, rank, counters);
   KP_LAUNCHED(ctx, 1);
