@@ -323,6 +323,7 @@ def main():
     launches = ctx.launches - launches0
     rel_vals = relevance(out)
     dom_ms, dom_n = ctx.stat("ms_" + work["what"]), ctx.stat("n_" + work["what"])
+    breakdown = {c: round(ctx.stat("ms_" + c) / max(args.steps, 1), 3) for c in ("pass", "flash", "transe_train", "update", "conv")}
     ctx.set_option("timing", 0)
 
     t = torch.tensor([t_kernel, t_e2e], dtype=torch.float64, device=device)
@@ -367,6 +368,7 @@ def main():
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": src,
                          "launches_timed": int(dom_n), "avg_launch_ms": (dom_ms / dom_n) if dom_n else None,
                          "share_of_step": dom_ms / t_kernel if t_kernel else None},
+            "kernel_ms_per_step": breakdown,  # CUDA-event time of the library's kernels by category (rank 0)
             "clocks": sampler.summary(w0, w1) if sampler else None,
             "relevance_checksum": float(np.nansum(rel_vals)),
         }

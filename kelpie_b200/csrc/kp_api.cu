@@ -36,6 +36,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_x4 = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_fc")) {
+    ctx->umma_fc = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "umma_rank")) {
     ctx->umma_rank = value;
     return KP_OK;

@@ -141,7 +141,20 @@ int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
   ctx->cv.ent_colsum = static_cast<float*>(cs);
   colsum_kernel<<<(D + 31) / 32, 1024>>>((int)ctx->N, D, ctx->ent, ctx->cv.ent_colsum);
   KP_LAUNCHED(ctx, 1);
+  if (D % 4 == 0 && w->hidden % 4 == 0) {  // split operands of the Linear layer for the tcgen05 GEMMs
+    if ((rc = kp_umma_b_prepare(ctx, ctx->cv.fc_w, D, w->hidden, false, &ctx->cv.fc_fwd, 0))) return rc;
+    if ((rc = kp_umma_b_prepare(ctx, ctx->cv.fc_w, w->hidden, D, true, &ctx->cv.fc_bwd, 0))) return rc;
+  }
   return KP_OK;
+}
+
+int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st) {
+  const int D = ctx->D, hidden = ctx->cv.hidden;
+  const kp_umma_b& B = forward ? ctx->cv.fc_fwd : ctx->cv.fc_bwd;
+  if (ctx->umma_fc && !ctx->force_simt && B.ready && M >= 128)
+    return kp_gemm_umma(ctx, A, forward ? hidden : D, M, B, C, forward ? D : hidden, ws_offset, st);
+  if (forward) return kp_sgemm(ctx, true, M, D, hidden, A, hidden, ctx->cv.fc_w, hidden, C, D, st);
+  return kp_sgemm(ctx, false, M, hidden, D, A, D, ctx->cv.fc_w, hidden, C, hidden, st);
 }
 
 int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32_t* rel_ids, int stride,
@@ -201,7 +214,7 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
       conve_conv_kernel<<<n, CV_THREADS, (size_t)40 * p.H * sizeof(float), st>>>(c);
     }
     KP_LAUNCHED(ctx, 1);
-    int rc = kp_sgemm(ctx, true, n, p.D, p.hidden, c.feat_out, p.hidden, p.fc_w, p.hidden, c.x_out, p.D, st);
+    int rc = kp_conve_fc(ctx, true, n, c.feat_out, c.x_out, feat_out ? 0 : (size_t)chunk * p.hidden * sizeof(float) + 1024, st);
     if (rc != KP_OK) return rc;
     conve_head_kernel<<<(int)(((size_t)n * p.D + 255) / 256), 256, 0, st>>>(c);
     KP_LAUNCHED(ctx, 1);

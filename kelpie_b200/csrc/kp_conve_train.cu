@@ -294,7 +294,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
       k.feat = feat; k.dfeat = dfeat; k.glhs = glhs;
       k.pair = pl.a_truth; k.seed = seed; k.step = (int)t; k.p_in = ctx->cv.drop_in; k.p_fm = ctx->cv.drop_fm;
       KP_LAUNCHED(ctx, 1);
-      if ((rc = kp_sgemm(ctx, false, (int)GA, hidden, D, dh, D, ctx->cv.fc_w, hidden, dfeat, hidden, st)) != KP_OK) return rc;
+      if ((rc = kp_conve_fc(ctx, false, (int)GA, dh, dfeat, 0, st)) != KP_OK) return rc;
       cv_backward<<<(int)GA, CT, back_smem, st>>>(k);
       KP_LAUNCHED(ctx, 1);
     }

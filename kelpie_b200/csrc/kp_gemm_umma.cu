@@ -1,0 +1,280 @@
+// fp32 GEMM  C[M, N] = A[M, K] * B[N, K]^T  on the tensor cores for the frozen ConvE network's Linear
+// layer (conve.py:50-52,150: forward x = feat W^T with K = 9728; backward dfeat = dh W, run as
+// dh (W^T)^T with K = 200), in the same bf16x3 split arithmetic as the fused pass: every fp32 operand
+// is hi + lo (two bf16), products hi*hi + hi*lo + lo*hi accumulate in fp32 in TMEM.
+//
+// cta_group::2 pairs: 256 rows of A (two 128-row tiles, one per SM) x 128 rows of B per accumulator
+// tile; each SM stages its own A rows and HALF of every B box; K-major operands by TMA through a
+// 6-slot ring; the accumulator is double-buffered in TMEM so the epilogue (one thread per row,
+// tcgen05.ld -> 128-bit global stores) overlaps the MMAs of the next tile.  B is split once
+// (kp_umma_b_prepare, weights are frozen); A is split per call into workspace arena 1.
+#include <cuda_bf16.h>
+
+#include "kp_internal.h"
+#include "kp_ptx.cuh"
+
+namespace {
+
+constexpr int GT = 192;
+constexpr int SLOT = 32768;
+constexpr int NSLOT = 6;
+
+struct GCtl {
+  uint64_t full[NSLOT], empty[NSLOT];
+  uint64_t s_full[2], s_free[2];
+  uint32_t tmem_base;
+};
+constexpr size_t G_SMEM = (size_t)NSLOT * SLOT + sizeof(GCtl) + 1024;
+
+struct GK_ {
+  int M, N, KB, n_tiles, tiles_per_strip;
+  float* C;
+  long long ldc;
+};
+
+__device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3fff);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3fff) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3fff) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT, 1)
+gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_constant__ CUtensorMap bl64_map,
+                 const __grid_constant__ CUtensorMap ah_map, const __grid_constant__ CUtensorMap al_map, const GK_ p) {
+  extern __shared__ uint8_t graw[];
+  uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(graw) + 1023) & ~uintptr_t(1023));
+  uint8_t* ring = sm;
+  GCtl* ctl = reinterpret_cast<GCtl*>(sm + (size_t)NSLOT * SLOT);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int strip = blockIdx.y, mtile = blockIdx.x;
+  const int t0 = strip * p.tiles_per_strip;
+  const int t1 = min(t0 + p.tiles_per_strip, p.n_tiles);
+  const int ntile = t1 - t0;
+  if (ntile <= 0) return;  // uniform over the pair
+  const uint32_t crank = ptx::cluster_ctarank();
+  const bool leader = crank == 0;
+
+  if (tid == 0) {
+    for (int s = 0; s < NSLOT; ++s) {
+      ptx::mbar_init(&ctl->full[s], 1);
+      ptx::mbar_init(&ctl->empty[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      ptx::mbar_init(&ctl->s_full[b], 1);
+      ptx::mbar_init(&ctl->s_free[b], 256);
+    }
+    ptx::fence_barrier_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc2(&ctl->tmem_base, 256);
+    ptx::tmem_relinquish2();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  ptx::tc_fence_after();
+  const uint32_t tm = ctl->tmem_base;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      ptx::prefetch_tmap(&bh64_map);
+      ptx::prefetch_tmap(&bl64_map);
+      ptx::prefetch_tmap(&ah_map);
+      ptx::prefetch_tmap(&al_map);
+      uint32_t use = 0;
+      auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row, uint32_t lo_off, uint32_t bytes_pair) {
+        const int s = use % NSLOT;
+        ptx::mbar_wait(&ctl->empty[s], ((use / NSLOT) & 1) ^ 1);
+        if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], bytes_pair);
+        const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&ctl->full[s]), 0);
+        uint8_t* dst = ring + (size_t)s * SLOT;
+        ptx::tma_load_2d_pair(dst, hi, bar, col, row);
+        ptx::tma_load_2d_pair(dst + lo_off, lo, bar, col, row);
+        ++use;
+      };
+      for (int i = 0; i < ntile; ++i)
+        for (int kb = 0; kb < p.KB; ++kb) {
+          load(&ah_map, &al_map, kb * 64, mtile * 128, 16384, 2 * 32768);                          // my 128 rows of A
+          load(&bh64_map, &bl64_map, kb * 64, (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the B tile
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && leader) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t ring_a = ptx::smem_u32(ring);
+      const uint64_t DK = udesc(0, 16, 1024);
+      uint32_t use = 0;
+      for (int i = 0; i < ntile; ++i) {
+        const int sb = i & 1;
+        const uint32_t d_s = tm + sb * 128;
+        if (i >= 2) {
+          ptx::mbar_wait_cluster(&ctl->s_free[sb], ((i >> 1) - 1) & 1);
+          ptx::tc_fence_after();
+        }
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::mbar_wait(&ctl->full[use % NSLOT], (use / NSLOT) & 1);
+          ptx::mbar_wait(&ctl->full[(use + 1) % NSLOT], ((use + 1) / NSLOT) & 1);
+          ptx::tc_fence_after();
+          const uint32_t a_hi = ring_a + (use % NSLOT) * SLOT, a_lo = a_hi + 16384;
+          const uint32_t b_hi = ring_a + ((use + 1) % NSLOT) * SLOT, b_lo = b_hi + 8192;
+          const uint64_t ah = DK + (a_hi >> 4), al = DK + (a_lo >> 4), bh = DK + (b_hi >> 4), bl = DK + (b_lo >> 4);
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc, 1u);
+            ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc, 1u);
+          }
+          ptx::umma2_commit_mc(&ctl->empty[use % NSLOT], 3);
+          ptx::umma2_commit_mc(&ctl->empty[(use + 1) % NSLOT], 3);
+          use += 2;
+        }
+        ptx::umma2_commit_mc(&ctl->s_full[sb], 3);
+      }
+    }
+  } else {
+    const int sub = warp & 3;
+    const int row = sub * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
+    const long long m = (long long)mtile * 128 + row;
+    const uint32_t s_free_leader0 = ptx::mapa_u32(ptx::smem_u32(&ctl->s_free[0]), 0);
+    for (int i = 0; i < ntile; ++i) {
+      const int sb = i & 1;
+      const int n0 = (t0 + i) * 128;
+      ptx::mbar_wait(&ctl->s_full[sb], (i >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t s_addr = tm + sb * 128 + lane_off;
+#pragma unroll 1
+      for (int c0 = 0; c0 < 128; c0 += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32(s_addr + c0, r);
+        ptx::tmem_ld_wait();
+        if (m < p.M) {
+          float* dst = p.C + m * p.ldc + n0 + c0;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4)
+            if (n0 + c0 + c < p.N)
+              *reinterpret_cast<float4*>(dst + c) =
+                  make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+        }
+      }
+      ptx::tc_fence_before();
+      ptx::mbar_arrive_cluster(s_free_leader0 + 8u * sb);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::cluster_sync_all();
+  if (warp == 1) ptx::tmem_dealloc2(tm, 256);
+}
+
+// fp32 [rows, cols] (ld) -> bf16 hi / lo [rows_pad, cols_pad] (zero padded)
+__global__ void split2_kernel(const float* __restrict__ src, long long rows, int cols, long long ld, long long rows_pad, int cols_pad,
+                              __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const long long total = rows_pad * (long long)(cols_pad / 2);
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / (cols_pad / 2);
+    const int c = (int)(i % (cols_pad / 2)) * 2;
+    float a = 0.f, b = 0.f;
+    if (r < rows) {
+      if (c < cols) a = src[r * ld + c];
+      if (c + 1 < cols) b = src[r * ld + c + 1];
+    }
+    const __nv_bfloat16 ah = __float2bfloat16_rn(a), bh = __float2bfloat16_rn(b);
+    reinterpret_cast<uint32_t*>(hi)[i] = pack2(ah, bh);
+    reinterpret_cast<uint32_t*>(lo)[i] = pack2(__float2bfloat16_rn(a - __bfloat162float(ah)), __float2bfloat16_rn(b - __bfloat162float(bh)));
+  }
+}
+// dst[c, r] = src[r, c]
+__global__ void transpose_kernel(const float* __restrict__ src, int rows, int cols, float* __restrict__ dst) {
+  __shared__ float t[32][33];
+  const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    if (r0 + j < rows && c0 + threadIdx.x < cols) t[j][threadIdx.x] = src[(size_t)(r0 + j) * cols + c0 + threadIdx.x];
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y)
+    if (c0 + j < cols && r0 + threadIdx.x < rows) dst[(size_t)(c0 + j) * rows + r0 + threadIdx.x] = t[threadIdx.x][j];
+}
+
+}  // namespace
+
+// B[N, K] fp32 (row-major, or its transpose when `transpose`: then the source is [K, N]) -> split tables + half-tile maps
+int kp_umma_b_prepare(kp_ctx* ctx, const float* B, int N, int K, bool transpose, kp_umma_b* out, cudaStream_t st) {
+  const long long Npad = ((long long)N + 127) / 128 * 128;
+  const int Kpad = (K + 63) / 64 * 64;
+  void *h = nullptr, *l = nullptr, *tmp = nullptr;
+  if (cudaMalloc(&h, (size_t)Npad * Kpad * 2) != cudaSuccess || cudaMalloc(&l, (size_t)Npad * Kpad * 2) != cudaSuccess)
+    KP_FAIL(ctx, KP_ENOMEM, "cannot allocate split GEMM operand (%lld x %d)", Npad, Kpad);
+  ctx->owned.push_back(h);
+  ctx->owned.push_back(l);
+  const float* src = B;
+  if (transpose) {
+    if (cudaMalloc(&tmp, (size_t)N * K * 4) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "cannot allocate transpose scratch");
+    transpose_kernel<<<dim3((N + 31) / 32, (K + 31) / 32), dim3(32, 8), 0, st>>>(B, K, N, (float*)tmp);  // src [K, N] -> [N, K]
+    KP_LAUNCHED(ctx, 1);
+    src = (const float*)tmp;
+  }
+  split2_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(src, N, K, K, Npad, Kpad, (__nv_bfloat16*)h, (__nv_bfloat16*)l);
+  KP_LAUNCHED(ctx, 1);
+  if (tmp) {
+    KP_CUDA(ctx, cudaStreamSynchronize(st));
+    cudaFree(tmp);
+  }
+  int rc;
+  if ((rc = kp_encode_2d(ctx, &out->hi64, h, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Kpad, Kpad, 64, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &out->lo64, l, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Kpad, Kpad, 64, 64, true)) != KP_OK) return rc;
+  out->N = N;
+  out->K = K;
+  out->Kpad = Kpad;
+  out->ready = true;
+  return KP_OK;
+}
+
+int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umma_b& B, float* C, long long ldc, size_t ws_offset,
+                 cudaStream_t st) {
+  if (M <= 0) return KP_OK;
+  if (B.N % 4 != 0 || ldc % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "tcgen05 GEMM needs N and ldc multiple of 4");
+  const int n_mt = ((M + 255) / 256) * 2;
+  const long long Mpad = (long long)n_mt * 128;
+  const size_t abytes = ((size_t)Mpad * B.Kpad * 2 + 1023) & ~size_t(1023);
+  int rc;
+  ws_offset = (ws_offset + 1023) & ~size_t(1023);  // the caller's own scratch at the start of arena 1 (may hold A itself)
+  if ((rc = kp_ws_reserve(ctx, ws_offset + 2 * abytes + 2048, 1)) != KP_OK) return rc;
+  __nv_bfloat16* ah = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1] + ws_offset);
+  __nv_bfloat16* al = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1] + ws_offset + abytes);
+  split2_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(A, M, B.K, lda, Mpad, B.Kpad, ah, al);
+  KP_LAUNCHED(ctx, 1);
+  CUtensorMap ah_map, al_map;
+  if ((rc = kp_encode_2d(ctx, &ah_map, ah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, B.Kpad, B.Kpad, 128, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &al_map, al, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, B.Kpad, B.Kpad, 128, 64, true)) != KP_OK) return rc;
+  GK_ p;
+  p.M = M;
+  p.N = B.N;
+  p.KB = B.Kpad / 64;
+  p.n_tiles = (B.N + 127) / 128;
+  int s = ctx->sm_count / n_mt;
+  if (s > p.n_tiles) s = p.n_tiles;
+  if (s < 1) s = 1;
+  p.tiles_per_strip = (p.n_tiles + s - 1) / s;
+  const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
+  p.C = C;
+  p.ldc = ldc;
+  static bool configured = false;
+  if (!configured) {
+    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    configured = true;
+  }
+  {
+    KpTimer timer(ctx, kp_ctx::T_CONV, st);
+    gemm_umma_kernel<<<dim3(n_mt, n_strips, 1), GT, G_SMEM, st>>>(B.hi64, B.lo64, ah_map, al_map, p);
+  }
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}

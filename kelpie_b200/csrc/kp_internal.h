@@ -9,6 +9,13 @@
 
 #include "../../include/kelpie_b200.h"
 
+// B operand of the tcgen05 fp32 GEMM (kp_gemm_umma.cu): split bf16 tables of a frozen [N, K] matrix
+struct kp_umma_b {
+  CUtensorMap hi64, lo64;  // box {64 k, 64 rows}
+  int N = 0, K = 0, Kpad = 0;
+  bool ready = false;
+};
+
 struct kp_ctx {
   int device = 0;
   int kind = 0;
@@ -35,6 +42,7 @@ struct kp_ctx {
     float* ent_colsum = nullptr;  // [D] column sums of the entity table
     int n_filters = 0, hidden = 0, H = 0;  // H = D / 20
     float drop_in = 0, drop_fm = 0, drop_hid = 0;
+    kp_umma_b fc_fwd, fc_bwd;  // Linear layer as B operands: W [D, hidden] (forward) and W^T [hidden, D] (backward)
   } cv;
 
   // split bf16 entity tables for the tcgen05 passes (built on first use, kp_flash_umma.cu)
@@ -60,6 +68,7 @@ struct kp_ctx {
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
   int64_t umma_x4 = 1;   // rows wider than 256 floats: clusters of two pairs that compute S once (kp_flash_umma4.cu)
+  int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
   int64_t umma_rotate = 1;  // rotating start of the entity walk (clusters share the table pass through L2)
   int* umma_cursor = nullptr;  // device [64]
@@ -200,3 +209,8 @@ int kp_umma_split_rows(kp_ctx* ctx, const float* mat, int G, long long Gpad, CUt
 // kp_rank_umma.cu: RANK epilogue of the DOT pass on the tensor cores; same counters as kp_pass_launch (bit-identical)
 bool kp_rank_umma_usable(kp_ctx* ctx, const kp_pass_args& a);
 int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st);
+int kp_umma_b_prepare(kp_ctx* ctx, const float* B, int N, int K, bool transpose, kp_umma_b* out, cudaStream_t st);
+int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umma_b& B, float* C, long long ldc, size_t ws_offset,
+                 cudaStream_t st);
+// ConvE Linear layer: forward (x = feat W^T) / backward (dfeat = dh W); tcgen05 from 128 rows on, else CUDA cores
+int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st);
