@@ -183,6 +183,21 @@ int kp_set_option(kp_ctx* ctx, const char* name, int64_t value);
  * cat in {pass, flash, transe_train, update, conv}.  Synchronises the recorded events. */
 int kp_stat(kp_ctx* ctx, const char* name, double* out);
 
+/* ---- full-model TransE training (verify_explanations retrains from scratch) ----------
+ * Replaces PairwiseRankingOptimizer.step_on_batch / optim.Adam (pairwise_ranking_optimizer.py:139-157,
+ * :46) over the whole entity and relation tables, which are DEVICE tensors updated in place.  The host
+ * draws every epoch's shuffle and corruptions in the reference's order (:100-118) and passes them as
+ * index tables: step k trains on rows [step_off[k], step_off[k+1]) of pos / neg ([rows, 3] int32, device).
+ * The Adam state and step counter live in the handle across calls (one call per epoch or per run). */
+typedef struct kp_fit kp_fit;
+int kp_transe_fit_create(int device, int64_t n_entities, int64_t n_relations2, int32_t dim, int32_t norm,
+                         float lr, float margin, float reg_weight, float* ent, float* rel, kp_fit** out);
+int kp_transe_fit_steps(kp_fit* fit, int64_t n_steps, const int64_t* step_off, const int32_t* pos,
+                        const int32_t* neg, float* loss_out, void* stream);
+int kp_transe_fit_destroy(kp_fit* fit);
+const char* kp_transe_fit_error(const kp_fit* fit); /* fit may be NULL: last create error */
+int64_t kp_transe_fit_launches(const kp_fit* fit);
+
 /* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
  * n_rows query vectors [n_rows, D] (device) against the resident entity table:
  *   out_m[g] = max_j z_gj (softmax: the reference max used, >= true max - 8),  out_l[g] = sum_j p_gj,

@@ -1,7 +1,8 @@
 """`Optimizer(model, hp, verbose).train(training_triples)` interface of the reference
 (src/link_prediction/optimization/*.py).  Only the Kelpie* subclasses -- the mimic
 post-training -- are on the hot path; they run as ONE job through the batched CUDA kernels
-(the engines batch many).  The full-model trainers stay with the reference.
+(the engines batch many).  Of the full-model trainers TransE's runs on the device
+(PairwiseRankingOptimizer.train); ComplEx's and ConvE's stay with the reference.
 """
 import numpy as np
 import torch
@@ -69,11 +70,60 @@ class _KelpieOptimizer(Optimizer):
 
 
 class PairwiseRankingOptimizer(Optimizer):
+    """Full-model TransE training (pairwise_ranking_optimizer.py:55-157), used by verify_explanations to
+    retrain from scratch: every epoch's shuffle / corruptions are drawn on the host in the reference's
+    order, the steps (margin-ranking loss + L2 + Adam over both tables) run in kp_transe_fit_steps."""
+
     def get_hyperparams_class():
         return PairwiseRankingOptimizerHyperParams
 
     def get_kelpie_class():
         return KelpiePairwiseRankingOptimizer
+
+    def train(self, training_triples, save_path=None, eval_every=-1, valid_triples=None, trial=None, patience=5):
+        hp, model = self.hp, self.model
+        if isinstance(model, KelpieModel):
+            raise Exception("the full-model trainer does not post-train a KelpieModel")
+        if not torch.cuda.is_available():
+            raise RuntimeError("kelpie_b200 has no CPU training path")
+        rows = np.vstack((np.asarray(training_triples), self.dataset.invert_triples(training_triples))).astype(np.int64)
+        model.invalidate_context()  # the scoring context borrows the tables that are about to change
+        model.cuda()
+        ent = model.entity_embeddings.data.contiguous()
+        rel = model.relation_embeddings.data.contiguous()
+        fit = runtime.TransEFit(ent, rel, model.norm, hp["lr"], hp["margin"], hp["regularizer_weight"])
+        n, bs, ratio = len(rows), int(hp["batch_size"]), int(hp["negative_triples_ratio"])
+        off = np.append(np.arange(0, n, bs), n).astype(np.int64)
+        best, bad = None, 0
+        self.epoch_losses = []
+        try:
+            for e in range(1, int(hp["epochs"]) + 1):
+                pos, neg = plans.draw_transe_full_epoch(rows, self.dataset.num_entities, ratio)
+                loss = fit.steps(pos, neg, off, want_loss=self.verbose)
+                if loss is not None:
+                    self.epoch_losses.append(float(loss.mean()))
+                if valid_triples is not None and eval_every > 0 and e % eval_every == 0:
+                    from ..evaluation import Evaluator
+                    torch.cuda.synchronize()
+                    h1 = Evaluator(model).evaluate(valid_triples)["h1"]
+                    model.invalidate_context()
+                    if trial is not None:
+                        trial.report(h1, e)
+                        if trial.should_prune():
+                            raise RuntimeError("trial pruned")
+                    if best is None or h1 > best:
+                        best, bad = h1, 0
+                    else:
+                        bad += 1
+                    if bad >= patience:
+                        break
+            self.launches = fit.launches()
+        finally:
+            fit.close()
+        model.entity_embeddings.data, model.relation_embeddings.data = ent, rel
+        model.invalidate_context()
+        if save_path is not None:
+            torch.save(model.state_dict(), save_path)
 
 
 class KelpiePairwiseRankingOptimizer(_KelpieOptimizer):

@@ -41,6 +41,23 @@ def draw_transe(facts, num_relations, n_ent_with_mimic, hp):
     return n, pos.reshape(-1, 3), neg.reshape(-1, 3)
 
 
+def draw_transe_full_epoch(rows, num_entities, ratio):
+    """One epoch of the FULL-model trainer (pairwise_ranking_optimizer.py:100-118): shuffles `rows` in place
+    (np.random, the state carries across epochs), then draws head_or_tail = randint(2) and the corrupting
+    entities = randint(num_entities) over ratio * n samples, of which -- like the training loop (:127-134) --
+    only the first n are used.  Returns (pos [n,3], neg [n,3]) int32."""
+    n = len(rows)
+    np.random.shuffle(rows)
+    coin = torch.randint(high=2, size=(ratio * n,))[:n].numpy()
+    rnd = torch.randint(high=num_entities, size=(ratio * n,))[:n].numpy()
+    pos = rows[np.arange(n) // ratio].astype(np.int32)
+    neg = pos.copy()
+    head = coin == 1
+    neg[head, 0] = rnd[head]
+    neg[~head, 2] = rnd[~head]
+    return pos, neg
+
+
 def draw_complex(facts, num_relations, hp):
     """multiclass_nll_optimizer.py:147-164.  Returns (rows_per_epoch, rows, static_epochs)."""
     rows = _rows_with_inverses(facts, num_relations)

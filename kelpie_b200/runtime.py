@@ -22,6 +22,7 @@ EXPORTS = [
     "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
     "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
     "kp_debug_contract",
+    "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
 ]
 
 
@@ -91,6 +92,17 @@ def load_library():
     lib.kp_stat.restype = c_int
     lib.kp_debug_contract.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.kp_debug_contract.restype = c_int
+    lib.kp_transe_fit_create.argtypes = [c_int, c_int64, c_int64, c_int32, c_int32, ctypes.c_float, ctypes.c_float,
+                                         ctypes.c_float, c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.kp_transe_fit_create.restype = c_int
+    lib.kp_transe_fit_steps.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.kp_transe_fit_steps.restype = c_int
+    lib.kp_transe_fit_destroy.argtypes = [c_void_p]
+    lib.kp_transe_fit_destroy.restype = c_int
+    lib.kp_transe_fit_error.argtypes = [c_void_p]
+    lib.kp_transe_fit_error.restype = c_char_p
+    lib.kp_transe_fit_launches.argtypes = [c_void_p]
+    lib.kp_transe_fit_launches.restype = c_int64
     _lib = lib
     return lib
 
@@ -294,3 +306,51 @@ def make_hp(kind, hp):
         h.optimizer, h.lr = OPT_ADAM, 1e-3
         h.label_smoothing = float(hp["label_smoothing"])
     return h
+
+
+class TransEFit:
+    """Full-model TransE trainer state (kp_transe_fit_*): Adam over the entity and relation tables, which are
+    CUDA fp32 tensors updated in place (pairwise_ranking_optimizer.py:139-157)."""
+
+    def __init__(self, ent, rel, norm, lr, margin, reg_weight):
+        self.lib = load_library()
+        if not (ent.is_cuda and rel.is_cuda and ent.is_contiguous() and rel.is_contiguous()
+                and ent.dtype == torch.float32 and rel.dtype == torch.float32):
+            raise RuntimeError("TransEFit needs contiguous CUDA fp32 tables (kelpie_b200 has no CPU path)")
+        self.ent, self.rel = ent, rel
+        self.device = ent.device
+        h = c_void_p()
+        rc = self.lib.kp_transe_fit_create(ent.device.index or 0, ent.shape[0], rel.shape[0], ent.shape[1], int(norm),
+                                           float(lr), float(margin), float(reg_weight), _ptr(ent), _ptr(rel), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"kp_transe_fit_create failed ({rc}): {self.lib.kp_transe_fit_error(None).decode()}")
+        self.handle = h
+
+    def steps(self, pos, neg, step_off, want_loss=False):
+        """pos / neg: [rows, 3] int32 (host or device); step_off: [n_steps + 1] row offsets (host)."""
+        pos = torch.as_tensor(pos, dtype=torch.int32).to(self.device).contiguous()
+        neg = torch.as_tensor(neg, dtype=torch.int32).to(self.device).contiguous()
+        off = np.ascontiguousarray(step_off, dtype=np.int64)
+        n = len(off) - 1
+        loss = torch.zeros(max(n, 1), dtype=torch.float32, device=self.device) if want_loss else None
+        rc = self.lib.kp_transe_fit_steps(self.handle, n, _np_ptr(off), _ptr(pos), _ptr(neg), _ptr(loss),
+                                          c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"kp_transe_fit_steps failed ({rc}): {self.lib.kp_transe_fit_error(self.handle).decode()}")
+        self._keep = (pos, neg)
+        return loss
+
+    def launches(self):
+        return int(self.lib.kp_transe_fit_launches(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.kp_transe_fit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

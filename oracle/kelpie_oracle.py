@@ -574,3 +574,42 @@ class Engine:
             rel = float(d_rank + _sigmoid(d))
             rels.append(rel / float(base["target_rank"]))
         return sum(rels) / len(rels)
+
+
+def train_transe_full(ent, rel, norm, training_triples, num_entities, num_relations, hp, n_epochs=None):
+    """Full-model TransE training: PairwiseRankingOptimizer.train / epoch / step_on_batch
+    (pairwise_ranking_optimizer.py:55-157) restated with torch autograd on the CPU; consumes np.random and the
+    torch CPU generator in the reference's order (shuffle, randint(2), randint(num_entities) per epoch).
+    ent / rel: float32 arrays; returns the trained copies."""
+    E = torch.nn.Parameter(torch.from_numpy(np.array(ent, dtype=np.float32)))
+    R = torch.nn.Parameter(torch.from_numpy(np.array(rel, dtype=np.float32)))
+    opt = torch.optim.Adam([E, R], lr=hp["lr"])
+    loss_fn = torch.nn.MarginRankingLoss(margin=hp["margin"], reduction="mean")
+    t = np.asarray(training_triples).astype(np.int64).reshape(-1, 3)
+    inv = t.copy()
+    inv[:, 0], inv[:, 2] = t[:, 2], t[:, 0]
+    inv[:, 1] = t[:, 1] + num_relations
+    rows = np.vstack((t, inv))
+    ratio, bs, w = int(hp["negative_triples_ratio"]), int(hp["batch_size"]), float(hp["regularizer_weight"])
+
+    def fwd(b):
+        lhs, rl, rhs = E[b[:, 0]], R[b[:, 1]], E[b[:, 2]]
+        return (lhs + rl - rhs).norm(p=norm, dim=1), (lhs, rl, rhs)
+
+    for _ in range(int(n_epochs if n_epochs is not None else hp["epochs"])):
+        np.random.shuffle(rows)
+        pos = torch.from_numpy(np.repeat(rows, ratio, axis=0))
+        size = torch.Size([len(pos)])
+        coin = torch.randint(high=2, size=size)
+        rnd = torch.randint(high=num_entities, size=size)
+        head = coin == 1
+        neg = torch.stack((torch.where(head, rnd, pos[:, 0]), pos[:, 1], torch.where(~head, rnd, pos[:, 2])), dim=1)
+        for b0 in range(0, len(rows), bs):
+            b1 = min(b0 + bs, len(rows))
+            opt.zero_grad()
+            ps, pf = fwd(pos[b0:b1])
+            ns, nf = fwd(neg[b0:b1])
+            loss = loss_fn(ps, ns, torch.tensor([-1.0])) + (_l2(pf, w) + _l2(nf, w)) / 2
+            loss.backward()
+            opt.step()
+    return E.detach().numpy(), R.detach().numpy()

@@ -1,0 +1,49 @@
+"""Full-model TransE training (kp_transe_fit_*) at configs/TransE_DBpedia50_training shape:
+device time per epoch and per step, algorithmic HBM bytes of the dense Adam update, next to the oracle
+restatement (= the reference's torch loop) on the host cores for a bounded sample of steps."""
+import sys, os, json, time, argparse
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from kelpie_b200 import plans, runtime
+from kelpie_b200.data import Dataset
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--epochs", type=int, default=10)
+ap.add_argument("--cpu-steps", type=int, default=20)
+a = ap.parse_args()
+ds = Dataset.from_npz(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "dbpedia50_ids.npz"), name="DBpedia50")
+N, R2, D = ds.num_entities, 2 * ds.num_relations, 256
+hp = dict(batch_size=2048, lr=0.01, margin=5, negative_triples_ratio=5, regularizer_weight=1.0)
+torch.manual_seed(0); np.random.seed(0)
+ent = torch.nn.init.xavier_normal_(torch.empty(N, D)).cuda()
+rel = torch.nn.init.xavier_normal_(torch.empty(R2, D)).cuda()
+rows = np.vstack((ds.training_triples, ds.invert_triples(ds.training_triples))).astype(np.int64)
+n = len(rows)
+off = np.append(np.arange(0, n, hp["batch_size"]), n).astype(np.int64)
+fit = runtime.TransEFit(ent, rel, 2, hp["lr"], hp["margin"], hp["regularizer_weight"])
+draws = [plans.draw_transe_full_epoch(rows, N, 5) for _ in range(a.epochs + 1)]
+dev = [(torch.from_numpy(p).cuda(), torch.from_numpy(q).cuda()) for p, q in draws]
+fit.steps(dev[0][0], dev[0][1], off); torch.cuda.synchronize()
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for p, q in dev[1:]:
+    fit.steps(p, q, off)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+steps = a.epochs * (len(off) - 1)
+adam_bytes = (N + R2) * D * 4 * 7  # g read + clear, m / v / p read + write
+out = {"shape": {"entities": N, "relations2": R2, "dim": D, "rows_per_epoch": n, "steps_per_epoch": len(off) - 1},
+       "gpu": {"ms_per_epoch": ms / a.epochs, "us_per_step": 1e3 * ms / steps, "steps_per_s": steps / (ms * 1e-3),
+               "adam_algorithmic_GBps_if_all_time_were_adam": adam_bytes / (ms / steps * 1e-3) / 1e9}}
+fit.close()
+# CPU: the oracle restatement (torch autograd + torch.optim.Adam, dense [N, D] gradient) on the host cores
+from oracle import kelpie_oracle as ko
+torch.set_num_threads(os.cpu_count())
+k = a.cpu_steps
+t0 = time.perf_counter()
+ko.train_transe_full(ent.cpu().numpy(), rel.cpu().numpy(), 2, ds.training_triples[: k * 1024], N, ds.num_relations,
+                     dict(hp, epochs=1), n_epochs=1)
+dt = time.perf_counter() - t0
+out["cpu_port"] = {"steps": k, "us_per_step": 1e6 * dt / k, "steps_per_s": k / dt, "cores": os.cpu_count()}
+out["speedup_steps_per_s"] = out["gpu"]["steps_per_s"] / out["cpu_port"]["steps_per_s"]
+print(json.dumps(out))
