@@ -139,6 +139,38 @@ class Dataset:
             else:
                 self.relation_to_type[r] = ONE_TO_ONE
 
+    # -- in-place edits used by verify_explanations (dataset.py:242-280) --------------------------
+    def add_training_triple(self, triple):
+        s, p, o = (int(x) for x in triple)
+        self._train = np.vstack((self._train, np.array([[s, p, o]], dtype=np.int64)))
+        self.entity_to_training_triples[s].append((s, p, o))
+        self.entity_to_training_triples[o].append((s, p, o))
+        self.entity_to_degree[s] = self.entity_to_degree.get(s, 0) + 1
+        self.entity_to_degree[o] = self.entity_to_degree.get(o, 0) + 1
+        self.to_filter[(s, p)].append(o)  # like the reference, only the direct key is maintained
+        self.train_to_filter[(s, p)].append(o)
+
+    def add_training_triples(self, triples):
+        for t in triples:
+            self.add_training_triple(t)
+
+    def remove_training_triple(self, triple):
+        s, p, o = (int(x) for x in triple)
+        t = self._train
+        self._train = t[~((t[:, 0] == s) & (t[:, 1] == p) & (t[:, 2] == o))]
+        self.entity_to_training_triples[s].remove((s, p, o))
+        if s != o:
+            self.entity_to_training_triples[o].remove((s, p, o))
+        self.entity_to_degree[s] -= 1
+        if s != o:
+            self.entity_to_degree[o] -= 1
+        self.to_filter[(s, p)].remove(o)
+        self.train_to_filter[(s, p)].remove(o)
+
+    def remove_training_triples(self, triples):
+        for t in set(tuple(int(x) for x in t) for t in triples):
+            self.remove_training_triple(t)
+
     def invert_triples(self, triples):
         """dataset.py:319-331."""
         t = np.asarray(triples)
