@@ -71,6 +71,11 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
   const bool leader = crank == 0;
   const int ngroup = p.groups_per_chunk;           // 128-dim groups of this chunk (<= 2)
   const int box0 = chunk * ngroup * 2;
+  // Work that only touches zero padding is skipped: S needs ceil(D / 16) k-steps, and when the pass is a single
+  // chunk its last dim group is contracted with N = the dims that are left, rounded up to 32 (each SM then
+  // stages n_last / 2 dims, starting at the group's base + rank * n_last / 2).
+  const int ksteps = (p.D + 15) / 16;
+  const int n_last = (gridDim.z == 1) ? min(128, ((p.D - 128 * (ngroup - 1) + 31) / 32) * 32) : 128;
 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
@@ -130,8 +135,9 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
             load(&eh64_map, &el64_map, kb * 64, tile_of(i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the entities
           }
         if (i > 0)
-          for (int g = 0; g < ngroup; ++g)
-            load(&eh_map, &el_map, (box0 + 2 * g + (int)crank) * 64, tile_of(i - 1) * 128, 16384, 2 * 32768);  // my 64 dims
+          for (int g = 0; g < ngroup; ++g)  // my half of the group's dims (64, or n_last / 2 of a trimmed last group)
+            load(&eh_map, &el_map, (box0 + 2 * g) * 64 + (int)crank * (g == ngroup - 1 ? n_last / 2 : 64), tile_of(i - 1) * 128, 16384,
+                 2 * 32768);
       }
     }
   } else if (warp == 1) {
@@ -139,6 +145,7 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
     if (lane == 0 && leader) {
       const uint32_t idesc_s = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc_pv_last = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | (((uint32_t)n_last >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t ring_a = ptx::smem_u32(ring);
       // descriptor templates: only the 14-bit start-address field changes between MMAs
       const uint64_t DK = udesc(0, 16, 1024), DMN = udesc(0, 16384, 1024);
@@ -154,14 +161,15 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           const uint32_t e_hi = ring_a + (use % NSLOT) * SLOT, e_lo = e_hi + 16384;
           const uint32_t d_o = TM_O + g * 128;
           const uint32_t p_t = TM_S + (t & 1) * 128;
+          const uint32_t idesc_g = (g == ngroup - 1) ? idesc_pv_last : idesc_pv;
           const uint64_t bh = DMN + (e_hi >> 4), bl = DMN + (e_lo >> 4);
 #pragma unroll
           for (int ks = 0; ks < 8; ++ks) {
             const uint32_t a_hi = p_t + 32 * (ks >> 1) + 8 * (ks & 1), a_lo = a_hi + 16;
             const uint64_t b_hi = bh + ks * (2048 >> 4), b_lo = bl + ks * (2048 >> 4);
-            ptx::umma2_bf16_ts(d_o, a_hi, b_hi, idesc_pv, (t > 0 || ks > 0) ? 1u : 0u);
-            ptx::umma2_bf16_ts(d_o, a_hi, b_lo, idesc_pv, 1u);
-            ptx::umma2_bf16_ts(d_o, a_lo, b_hi, idesc_pv, 1u);
+            ptx::umma2_bf16_ts(d_o, a_hi, b_hi, idesc_g, (t > 0 || ks > 0) ? 1u : 0u);
+            ptx::umma2_bf16_ts(d_o, a_hi, b_lo, idesc_g, 1u);
+            ptx::umma2_bf16_ts(d_o, a_lo, b_hi, idesc_g, 1u);
           }
           release(use);
           ++use;
@@ -181,6 +189,7 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
+            if (kb * 4 + kk >= ksteps) break;  // only zero padding beyond D
             ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
             ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
             ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc_s, 1u);

@@ -248,6 +248,7 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       const uint32_t idesc_pv = (1u << 4) | (1u << 7) | (1u << 10) | (1u << 16) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t ring_a = ptx::smem_u32(ring);
       const uint64_t DK = udesc(0, 16, 1024), DMN = udesc(0, 16384, 1024);
+      const int ksteps = (p.D + 15) / 16;
       uint32_t use = 0;
       long long w_slot = 0, w_own = 0, w_for = 0;
       const long long t_begin = clock64();
@@ -269,6 +270,7 @@ flash_umma4_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
           const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
+            if (kb * 4 + kk >= ksteps) break;  // only zero padding beyond D
             ptx::umma2_bf16(TM_A, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
             ptx::umma2_bf16(TM_A, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
             ptx::umma2_bf16(TM_A, al + kk * 2, bh + kk * 2, idesc_s, 1u);

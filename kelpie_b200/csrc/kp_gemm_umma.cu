@@ -27,7 +27,7 @@ struct GCtl {
 constexpr size_t G_SMEM = (size_t)NSLOT * SLOT + sizeof(GCtl) + 1024;
 
 struct GK_ {
-  int M, N, KB, n_tiles, tiles_per_strip;
+  int M, N, KB, ksteps, n_tiles, tiles_per_strip;
   float* C;
   long long ldc;
 };
@@ -128,6 +128,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
           const uint64_t ah = DK + (a_hi >> 4), al = DK + (a_lo >> 4), bh = DK + (b_hi >> 4), bl = DK + (b_lo >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
+            if (kb * 4 + kk >= p.ksteps) break;  // only zero padding beyond K
             ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
             ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc, 1u);
             ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc, 1u);
@@ -258,6 +259,7 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   p.M = M;
   p.N = B.N;
   p.KB = B.Kpad / 64;
+  p.ksteps = (B.K + 15) / 16;
   p.n_tiles = (B.N + 127) / 128;
   int s = ctx->sm_count / n_mt;
   if (s > p.n_tiles) s = p.n_tiles;

@@ -150,6 +150,7 @@ rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_cons
           const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
+            if (kb * 4 + kk >= (p.D + 15) / 16) break;  // only zero padding beyond D
             ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
             ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
             ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc_s, 1u);
