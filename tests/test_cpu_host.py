@@ -179,3 +179,42 @@ def test_sharded_engine_two_gloo_ranks(tmp_path):
     for p in procs:
         out, _ = p.communicate(timeout=120)
         assert p.returncode == 0, out
+
+
+def test_full_epoch_draw_matches_reference_order():
+    """plans.draw_transe_full_epoch = pairwise_ranking_optimizer.py:100-118: shuffle, randint(2), randint(N) over
+    ratio * n samples, first n used."""
+    import torch
+    from kelpie_b200 import plans
+    rng = np.random.default_rng(0)
+    rows = np.stack([rng.integers(0, 50, 37), rng.integers(0, 6, 37), rng.integers(0, 50, 37)], 1).astype(np.int64)
+    a = rows.copy()
+    np.random.seed(4); torch.manual_seed(4)
+    pos, neg = plans.draw_transe_full_epoch(a, 50, 5)
+    b = rows.copy()
+    np.random.seed(4); torch.manual_seed(4)
+    np.random.shuffle(b)
+    rep = np.repeat(b, 5, axis=0)
+    coin = torch.randint(high=2, size=(len(rep),)).numpy()
+    rnd = torch.randint(high=50, size=(len(rep),)).numpy()
+    want_neg = rep.copy()
+    want_neg[coin == 1, 0] = rnd[coin == 1]
+    want_neg[coin != 1, 2] = rnd[coin != 1]
+    assert np.array_equal(a, b)                       # shuffled in place, state carries to the next epoch
+    assert np.array_equal(pos, rep[:37]) and np.array_equal(neg, want_neg[:37])
+
+
+def test_dataset_edits_follow_reference_semantics():
+    """dataset.py:242-280: add / remove keep train array, per-entity lists, degrees and the DIRECT filter key."""
+    from kelpie_b200.data import Dataset
+    train = np.array([[0, 0, 1], [0, 0, 2], [1, 1, 2], [3, 0, 1]])
+    ds = Dataset("t", train, np.zeros((0, 3), int), np.array([[2, 1, 3]]), 4, 2)
+    ds.remove_training_triples([(0, 0, 2), (0, 0, 2)])
+    assert len(ds.training_triples) == 3 and (0, 0, 2) not in ds.entity_to_training_triples[0]
+    assert ds.to_filter[(0, 0)] == [1] and ds.train_to_filter[(0, 0)] == [1]
+    assert ds.entity_to_degree[0] == 1 and ds.entity_to_degree[2] == 1
+    ds.add_training_triples([(2, 0, 3)])
+    assert tuple(ds.training_triples[-1]) == (2, 0, 3) and ds.to_filter[(2, 0)] == [3]
+    assert (2, 0, 3) in ds.entity_to_training_triples[3] and ds.entity_to_degree[3] == 2
+    with pytest.raises(ValueError):
+        ds.remove_training_triple((1, 0, 0))           # like list.remove in the reference
