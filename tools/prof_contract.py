@@ -23,12 +23,16 @@ ctx.contract(q, a.mode); torch.cuda.synchronize()
 torch.cuda.synchronize()
 ctx.set_option("umma_prof", 1)
 ctx.set_option("timing", 1); ctx.stat("reset")
+w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+w0.record()
 for _ in range(a.reps):
     ctx.contract(q, a.mode)
+w1.record()
 torch.cuda.synchronize()
+wall = w0.elapsed_time(w1) / a.reps  # whole call on the caller's stream (query split + every launch + merge)
 ms = ctx.stat("ms_flash") / ctx.stat("n_flash")
 fl = 4.0 * a.G * a.N * a.D
-out = {"ms": ms, "tflops_alg": fl / ms / 1e9}
+out = {"ms": ms, "tflops_alg": fl / ms / 1e9, "call_ms": wall, "call_tflops_alg": fl / wall / 1e9}
 try:
     tot = ctx.stat("umma_prof_total")
     n_qt = (a.G + 255) // 256 * 2
