@@ -247,13 +247,13 @@ int kp_flash_max_strips(kp_ctx* ctx) {
 }
 
 // Upper bound on n_strips(g) * g over every row count g <= G a caller may run the pass with:
-// CUDA-core path (g < 32), tcgen05 path with CTAs <= SMs (strips * query tiles <= SMs) and with
-// more CTAs than SMs (<= 8 strips, chosen against wave quantisation).
+// CUDA-core path (g < 32), tcgen05 path with less than a wave per strip (strips * clusters <= ~4 waves, plus
+// rounding: <= 5 SMs x 128 rows) and with more (<= 8 strips, chosen against wave quantisation).
 size_t kp_flash_part_rows(kp_ctx* ctx, int G) {
   int a = 1;
   kp_flash_plan(ctx, 16, &a);
   size_t rows = (size_t)a * (size_t)(G < 32 ? G : 32);
-  const size_t few = (size_t)64 * G < (size_t)ctx->sm_count * 128 ? (size_t)64 * G : (size_t)ctx->sm_count * 128;
+  const size_t few = (size_t)64 * G < (size_t)ctx->sm_count * 640 ? (size_t)64 * G : (size_t)ctx->sm_count * 640;
   if (few > rows) rows = few;
   if ((size_t)8 * G > rows) rows = (size_t)8 * G;
   return rows + (size_t)G;  // slack for the CUDA-core plan's rounding (strips = ceil(2 SMs / query tiles))

@@ -349,26 +349,24 @@ UPlan umma_plan(kp_ctx* ctx, int G) {
   u.n_tiles = (int)((ctx->N + 127) / 128);
   u.quad = u.pair && u.cc == 2 && ctx->umma_x4 != 0;
   const int sms = u.quad ? kp_flash_umma4_sms(ctx) : ctx->sm_count;
-  int s = sms / (u.n_qt * u.cc);
-  if (s > 64) s = 64;
-  if (s < 1) {
-    // more CTAs than SMs: pick the strip count (<= 8) whose last wave is fullest
-    const int unit = u.quad ? 4 : (u.pair ? 2 : 1);           // CTAs that must be co-resident
-    const long long units = (long long)u.n_qt * u.cc / unit;  // per strip
-    const long long slots = sms / unit;
-    double best = 0.0;
-    s = 1;
-    for (int c = 1; c <= 8; ++c) {
-      const long long waves = (units * c + slots - 1) / slots;
-      const double eff = (double)(units * c) / (double)(waves * slots);
-      if (eff > best + 0.02) {
-        best = eff;
-        s = c;
-      }
+  // Strip count: the entity range is cut into `s` strips so that (query-tile clusters x strips) fills whole waves
+  // of the SMs the launch can occupy.  unit = CTAs that must be co-resident, units = clusters per strip.
+  const int unit = u.quad ? 4 : (u.pair ? 2 : 1);
+  const long long units = ((long long)u.n_qt * u.cc + unit - 1) / unit;
+  const long long slots = sms / unit > 0 ? sms / unit : 1;
+  long long cmax = units >= slots ? 8 : 4 * slots / units;  // less than a wave per strip: up to ~4 waves in total
+  if (cmax > 64) cmax = 64;
+  if (cmax > u.n_tiles) cmax = u.n_tiles;
+  int s = 1;
+  double best = 0.0;
+  for (int c = 1; c <= (int)cmax; ++c) {
+    const long long waves = (units * c + slots - 1) / slots;
+    const double eff = (double)(units * c) / (double)(waves * slots);
+    if (eff > best + 0.02) {
+      best = eff;
+      s = c;
     }
   }
-  if (s > u.n_tiles) s = u.n_tiles;
-  if (s < 1) s = 1;
   u.tps = (u.n_tiles + s - 1) / s;
   u.n_strips = (u.n_tiles + u.tps - 1) / u.tps;
   return u;

@@ -287,7 +287,9 @@ int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;
-  p.cursor = ctx->umma_rotate ? ctx->umma_cursor : nullptr;
+  // two dim chunks = two clusters per (query tiles, strip) whose lazy reference maxima must agree: they have to
+  // visit the tiles in the same order, so the rotating start is only used by the single-chunk pass
+  p.cursor = (ctx->umma_rotate && n_chunks == 1) ? ctx->umma_cursor : nullptr;
   static bool configured = false;
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U2_SMEM));
