@@ -353,20 +353,7 @@ UPlan umma_plan(kp_ctx* ctx, int G) {
   // of the SMs the launch can occupy.  unit = CTAs that must be co-resident, units = clusters per strip.
   const int unit = u.quad ? 4 : (u.pair ? 2 : 1);
   const long long units = ((long long)u.n_qt * u.cc + unit - 1) / unit;
-  const long long slots = sms / unit > 0 ? sms / unit : 1;
-  long long cmax = units >= slots ? 8 : 4 * slots / units;  // less than a wave per strip: up to ~4 waves in total
-  if (cmax > 64) cmax = 64;
-  if (cmax > u.n_tiles) cmax = u.n_tiles;
-  int s = 1;
-  double best = 0.0;
-  for (int c = 1; c <= (int)cmax; ++c) {
-    const long long waves = (units * c + slots - 1) / slots;
-    const double eff = (double)(units * c) / (double)(waves * slots);
-    if (eff > best + 0.02) {
-      best = eff;
-      s = c;
-    }
-  }
+  const int s = kp_plan_strips(units, sms / unit, u.n_tiles);
   u.tps = (u.n_tiles + s - 1) / s;
   u.n_strips = (u.n_tiles + u.tps - 1) / u.tps;
   return u;

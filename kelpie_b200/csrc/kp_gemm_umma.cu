@@ -261,9 +261,7 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   p.KB = B.Kpad / 64;
   p.ksteps = (B.K + 15) / 16;
   p.n_tiles = (B.N + 127) / 128;
-  int s = ctx->sm_count / n_mt;
-  if (s > p.n_tiles) s = p.n_tiles;
-  if (s < 1) s = 1;
+  const int s = kp_plan_strips(n_mt / 2, ctx->sm_count / 2, p.n_tiles);
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
   p.C = C;

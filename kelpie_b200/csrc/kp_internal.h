@@ -214,3 +214,25 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
                  cudaStream_t st);
 // ConvE Linear layer: forward (x = feat W^T) / backward (dfeat = dh W); tcgen05 from 128 rows on, else CUDA cores
 int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st);
+
+// Strip count for a launch of `units` co-resident CTA groups per strip on `slots` group slots: the entity (or
+// column) range is cut into s strips so that units * s fills whole waves.  Less than a wave per strip: up to
+// ~4 waves in total; otherwise at most 8 strips, chosen against wave quantisation.
+inline int kp_plan_strips(long long units, long long slots, long long n_tiles) {
+  if (units < 1) units = 1;
+  if (slots < 1) slots = 1;
+  long long cmax = units >= slots ? 8 : 4 * slots / units;
+  if (cmax > 64) cmax = 64;
+  if (cmax > n_tiles) cmax = n_tiles;
+  int s = 1;
+  double best = 0.0;
+  for (int c = 1; c <= (int)cmax; ++c) {
+    const long long waves = (units * c + slots - 1) / slots;
+    const double eff = (double)(units * c) / (double)(waves * slots);
+    if (eff > best + 0.02) {
+      best = eff;
+      s = c;
+    }
+  }
+  return s;
+}

@@ -389,10 +389,7 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   p.D = D;
   p.KB = (D + 63) / 64;
   p.n_tiles = (int)((ctx->N + 127) / 128);
-  int s = ctx->sm_count / n_qt;
-  if (s > 64) s = 64;
-  if (s > p.n_tiles) s = p.n_tiles;
-  if (s < 1) s = 1;
+  const int s = kp_plan_strips(n_qt / 2, ctx->sm_count / 2, p.n_tiles);
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
   p.kappa = ldexpf(1.f, -16) + (float)D * ldexpf(1.f, -22);
