@@ -198,6 +198,21 @@ int kp_transe_fit_destroy(kp_fit* fit);
 const char* kp_transe_fit_error(const kp_fit* fit); /* fit may be NULL: last create error */
 int64_t kp_transe_fit_launches(const kp_fit* fit);
 
+/* Full-model ComplEx training: MultiClassNLLOptimizer.step_on_batch (multiclass_nll_optimizer.py:123-135) with
+ * ComplEx.forward (complex.py:58-86), CrossEntropyLoss(mean) and optim.Adagrad / Adam / SGD (:41-48) over both
+ * tables (device, updated in place).  optimizer: 0 Adagrad, 1 Adam (betas = decay1, decay2), 2 SGD.  reg_weight must
+ * be 0 (as in every shipped config).  rows: [total, 3] int32 (device), already permuted by the host in the
+ * reference's order (torch.randperm per epoch, :110-111); step k = rows [step_off[k], step_off[k+1]). */
+typedef struct kp_cfit kp_cfit;
+int kp_complex_fit_create(int device, int64_t n_entities, int64_t n_relations2, int32_t dim, int32_t optimizer,
+                          float lr, float beta1, float beta2, float reg_weight, int32_t max_batch, float* ent,
+                          float* rel, kp_cfit** out);
+int kp_complex_fit_steps(kp_cfit* fit, int64_t n_steps, const int64_t* step_off, const int32_t* rows,
+                         float* loss_out, void* stream);
+int kp_complex_fit_destroy(kp_cfit* fit);
+const char* kp_complex_fit_error(const kp_cfit* fit); /* fit may be NULL: last create error */
+int64_t kp_complex_fit_launches(const kp_cfit* fit);
+
 /* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
  * n_rows query vectors [n_rows, D] (device) against the resident entity table:
  *   out_m[g] = max_j z_gj (softmax: the reference max used, >= true max - 8),  out_l[g] = sum_j p_gj,

@@ -27,7 +27,7 @@ struct GCtl {
 constexpr size_t G_SMEM = (size_t)NSLOT * SLOT + sizeof(GCtl) + 1024;
 
 struct GK_ {
-  int M, N, KB, ksteps, n_tiles, tiles_per_strip;
+  int M, N, KB, ksteps, n_tiles, tiles_per_strip, kb_per_split;  // kb_per_split > 0: split-K over blockIdx.z, C accumulated with reductions
   float* C;
   long long ldc;
 };
@@ -61,6 +61,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
   if (ntile <= 0) return;  // uniform over the pair
   const uint32_t crank = ptx::cluster_ctarank();
   const bool leader = crank == 0;
+  const int kb0 = p.kb_per_split > 0 ? (int)blockIdx.z * p.kb_per_split : 0;
+  const int kb1 = p.kb_per_split > 0 ? min(kb0 + p.kb_per_split, p.KB) : p.KB;
+  if (kb0 >= kb1) return;  // uniform over the pair
 
   if (tid == 0) {
     for (int s = 0; s < NSLOT; ++s) {
@@ -101,7 +104,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
         ++use;
       };
       for (int i = 0; i < ntile; ++i)
-        for (int kb = 0; kb < p.KB; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           load(&ah_map, &al_map, kb * 64, mtile * 128, 16384, 2 * 32768);                          // my 128 rows of A
           load(&bh64_map, &bl64_map, kb * 64, (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the B tile
         }
@@ -119,7 +122,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
           ptx::mbar_wait_cluster(&ctl->s_free[sb], ((i >> 1) - 1) & 1);
           ptx::tc_fence_after();
         }
-        for (int kb = 0; kb < p.KB; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           ptx::mbar_wait(&ctl->full[use % NSLOT], (use / NSLOT) & 1);
           ptx::mbar_wait(&ctl->full[(use + 1) % NSLOT], ((use + 1) / NSLOT) & 1);
           ptx::tc_fence_after();
@@ -129,7 +132,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (kb * 4 + kk >= p.ksteps) break;  // only zero padding beyond K
-            ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > 0 || kk > 0) ? 1u : 0u);
+            ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
             ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc, 1u);
             ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc, 1u);
           }
@@ -161,9 +164,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
           float* dst = p.C + m * p.ldc + n0 + c0;
 #pragma unroll
           for (int c = 0; c < 32; c += 4)
-            if (n0 + c0 + c < p.N)
-              *reinterpret_cast<float4*>(dst + c) =
-                  make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+            if (n0 + c0 + c < p.N) {
+              if (p.kb_per_split > 0)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(__uint_as_float(r[c])),
+                             "f"(__uint_as_float(r[c + 1])), "f"(__uint_as_float(r[c + 2])), "f"(__uint_as_float(r[c + 3]))
+                             : "memory");
+              else
+                *reinterpret_cast<float4*>(dst + c) =
+                    make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
+            }
         }
       }
       ptx::tc_fence_before();
@@ -204,7 +213,99 @@ __global__ void transpose_kernel(const float* __restrict__ src, int rows, int co
     if (c0 + j < cols && r0 + threadIdx.x < rows) dst[(size_t)(c0 + j) * rows + r0 + threadIdx.x] = t[threadIdx.x][j];
 }
 
+// fp32 src [cols, rows] (ld): the TRANSPOSE -> bf16 hi / lo [rows_pad, cols_pad] (zero padded); 32x32 tiles through shared memory
+__global__ void split2t_kernel(const float* __restrict__ src, long long rows, int cols, long long ld, long long rows_pad, int cols_pad,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {  // src row = c0 + j (a column of the result), src col = r0 + x
+    const long long sr = c0 + j, sc = r0 + threadIdx.x;
+    t[j][threadIdx.x] = (sr < cols && sc < rows) ? src[sr * ld + sc] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {  // result row r0 + j, col c0 + x
+    const long long r = r0 + j;
+    const int c = c0 + threadIdx.x;
+    if (r < rows_pad && c < cols_pad) {
+      const float a = t[threadIdx.x][j];
+      const __nv_bfloat16 ah = __float2bfloat16_rn(a);
+      hi[r * cols_pad + c] = ah;
+      lo[r * cols_pad + c] = __float2bfloat16_rn(a - __bfloat162float(ah));
+    }
+  }
+}
+
 }  // namespace
+
+// C[M, N] = opA(A) * opB(B)^T with both operands given per call (fp32, split into workspace arena 1 behind `ws_offset`):
+// opA(A) = A [M, K] (lda) or, transA, the transpose of A [K, M];  opB(B) = B [N, K] (ldb) or, transB, the transpose of B [K, N].
+// A long K with few output tiles is cut over blockIdx.z and accumulated with fp32 reductions into a zeroed C.
+int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, int M, const float* B, long long ldb, bool transB,
+                     int N, int K, float* C, long long ldc, size_t ws_offset, cudaStream_t st) {
+  if (M <= 0 || N <= 0 || K <= 0) return KP_OK;
+  const int Nc = (N + 3) & ~3;  // columns are stored four at a time: the (zero) padding up to Nc is written too
+  if (ldc % 4 != 0 || ldc < Nc) KP_FAIL(ctx, KP_EINVAL, "tcgen05 GEMM needs ldc a multiple of 4 and >= N rounded up to 4");
+  const int n_mt = ((M + 255) / 256) * 2;
+  const long long Mpad = (long long)n_mt * 128, Npad = ((long long)N + 127) / 128 * 128;
+  const int Kpad = (K + 63) / 64 * 64;
+  const size_t abytes = ((size_t)Mpad * Kpad * 2 + 1023) & ~size_t(1023), bbytes = ((size_t)Npad * Kpad * 2 + 1023) & ~size_t(1023);
+  int rc;
+  ws_offset = (ws_offset + 1023) & ~size_t(1023);
+  if ((rc = kp_ws_reserve(ctx, ws_offset + 2 * abytes + 2 * bbytes + 2048, 1)) != KP_OK) return rc;
+  char* base = ctx->ws_arena[1] + ws_offset;
+  __nv_bfloat16 *ah = (__nv_bfloat16*)base, *al = (__nv_bfloat16*)(base + abytes);
+  __nv_bfloat16 *bh = (__nv_bfloat16*)(base + 2 * abytes), *bl = (__nv_bfloat16*)(base + 2 * abytes + bbytes);
+  auto split = [&](const float* src, long long ld, bool trans, long long rows, long long rows_pad, __nv_bfloat16* h, __nv_bfloat16* l) {
+    if (trans)
+      split2t_kernel<<<dim3((unsigned)((rows_pad + 31) / 32), (unsigned)((Kpad + 31) / 32)), dim3(32, 8), 0, st>>>(src, rows, K, ld, rows_pad,
+                                                                                                           Kpad, h, l);
+    else
+      split2_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(src, rows, K, ld, rows_pad, Kpad, h, l);
+  };
+  split(A, lda, transA, M, Mpad, ah, al);
+  split(B, ldb, transB, N, Npad, bh, bl);
+  KP_LAUNCHED(ctx, 2);
+  CUtensorMap ah_map, al_map, bh_map, bl_map;
+  if ((rc = kp_encode_2d(ctx, &ah_map, ah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, Kpad, Kpad, 128, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &al_map, al, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, Kpad, Kpad, 128, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &bh_map, bh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Kpad, Kpad, 64, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &bl_map, bl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Kpad, Kpad, 64, 64, true)) != KP_OK) return rc;
+  GK_ p;
+  p.M = M;
+  p.N = Nc;
+  p.KB = Kpad / 64;
+  p.ksteps = (K + 15) / 16;
+  p.n_tiles = (N + 127) / 128;
+  const int s = kp_plan_strips(n_mt / 2, ctx->sm_count / 2, p.n_tiles);
+  p.tiles_per_strip = (p.n_tiles + s - 1) / s;
+  const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
+  int ksplit = 1;
+  const long long clusters = (long long)(n_mt / 2) * n_strips;
+  if (clusters * 2 <= ctx->sm_count / 2 && p.KB >= 16) {  // under half a wave and a long K: split it
+    ksplit = (int)((ctx->sm_count / 2) / clusters);
+    if (ksplit > p.KB / 8) ksplit = p.KB / 8;
+    if (ksplit < 1) ksplit = 1;
+  }
+  p.kb_per_split = ksplit > 1 ? (p.KB + ksplit - 1) / ksplit : 0;
+  if (ksplit > 1) {
+    ksplit = (p.KB + p.kb_per_split - 1) / p.kb_per_split;
+    KP_CUDA(ctx, cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Nc * 4, (size_t)M, st));
+  }
+  p.C = C;
+  p.ldc = ldc;
+  static bool configured = false;
+  if (!configured) {
+    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    configured = true;
+  }
+  {
+    KpTimer timer(ctx, kp_ctx::T_CONV, st);
+    gemm_umma_kernel<<<dim3(n_mt, n_strips, ksplit), GT, G_SMEM, st>>>(bh_map, bl_map, ah_map, al_map, p);
+  }
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}
 
 // B[N, K] fp32 (row-major, or its transpose when `transpose`: then the source is [K, N]) -> split tables + half-tile maps
 int kp_umma_b_prepare(kp_ctx* ctx, const float* B, int N, int K, bool transpose, kp_umma_b* out, cudaStream_t st) {
@@ -260,6 +361,7 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   p.N = B.N;
   p.KB = B.Kpad / 64;
   p.ksteps = (B.K + 15) / 16;
+  p.kb_per_split = 0;
   p.n_tiles = (B.N + 127) / 128;
   const int s = kp_plan_strips(n_mt / 2, ctx->sm_count / 2, p.n_tiles);
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;

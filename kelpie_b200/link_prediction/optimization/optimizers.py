@@ -1,8 +1,8 @@
 """`Optimizer(model, hp, verbose).train(training_triples)` interface of the reference
 (src/link_prediction/optimization/*.py).  Only the Kelpie* subclasses -- the mimic
 post-training -- are on the hot path; they run as ONE job through the batched CUDA kernels
-(the engines batch many).  Of the full-model trainers TransE's runs on the device
-(PairwiseRankingOptimizer.train); ComplEx's and ConvE's stay with the reference.
+(the engines batch many).  Of the full-model trainers TransE's and ComplEx's run on the
+device (PairwiseRankingOptimizer.train, MultiClassNLLOptimizer.train); ConvE's stays with the reference.
 """
 import numpy as np
 import torch
@@ -131,11 +131,66 @@ class KelpiePairwiseRankingOptimizer(_KelpieOptimizer):
 
 
 class MultiClassNLLOptimizer(Optimizer):
+    """Full-model ComplEx training (multiclass_nll_optimizer.py:58-135), used by verify_explanations to retrain
+    from scratch: every epoch's permutation is drawn on the host (torch.randperm, the reference's order), the
+    steps (1-vs-all cross-entropy against the whole entity table + Adagrad / Adam / SGD over both tables) run in
+    kp_complex_fit_steps on the tensor cores."""
+
     def get_hyperparams_class():
         return MultiClassNLLOptimizerHyperParams
 
     def get_kelpie_class():
         return KelpieMultiClassNLLOptimizer
+
+    def train(self, training_triples, save_path=None, eval_every=-1, valid_triples=None, trial=None, patience=5):
+        hp, model = self.hp, self.model
+        if isinstance(model, KelpieModel):
+            raise Exception("the full-model trainer does not post-train a KelpieModel")
+        if not torch.cuda.is_available():
+            raise RuntimeError("kelpie_b200 has no CPU training path")
+        rows = np.vstack((np.asarray(training_triples), self.dataset.invert_triples(training_triples))).astype(np.int64)
+        n = len(rows)
+        bs = min(int(hp["batch_size"]), n)  # :70
+        model.invalidate_context()
+        model.cuda()
+        ent = model.entity_embeddings.data.contiguous()
+        rel = model.relation_embeddings.data.contiguous()
+        fit = runtime.ComplExFit(ent, rel, hp["optimizer_name"], hp["lr"], hp["decay1"], hp["decay2"],
+                                 hp["regularizer_weight"], bs)
+        starts = np.arange(0, n, int(hp["batch_size"]))  # batch_start += self.batch_size (:119)
+        off = np.append(starts, n).astype(np.int64)
+        keep = np.minimum(off[1:], off[:-1] + bs) == off[1:]
+        assert keep.all()
+        best, bad = None, 0
+        self.epoch_losses = []
+        try:
+            for e in range(1, int(hp["epochs"]) + 1):
+                perm = torch.randperm(n).numpy()
+                loss = fit.steps(rows[perm].astype(np.int32), off, want_loss=self.verbose)
+                if loss is not None:
+                    self.epoch_losses.append(float(loss.mean()))
+                if valid_triples is not None and eval_every > 0 and (e + 1) % eval_every == 0:  # :76
+                    from ..evaluation import Evaluator
+                    torch.cuda.synchronize()
+                    h1 = Evaluator(model).evaluate(valid_triples)["h1"]
+                    model.invalidate_context()
+                    if trial is not None:
+                        trial.report(h1, e)
+                        if trial.should_prune():
+                            raise RuntimeError("trial pruned")
+                    if best is None or h1 > best:
+                        best, bad = h1, 0
+                    else:
+                        bad += 1
+                    if bad >= patience:
+                        break
+            self.launches = fit.launches()
+        finally:
+            fit.close()
+        model.entity_embeddings.data, model.relation_embeddings.data = ent, rel
+        model.invalidate_context()
+        if save_path is not None:
+            torch.save(model.state_dict(), save_path)
 
 
 class KelpieMultiClassNLLOptimizer(_KelpieOptimizer):

@@ -23,6 +23,7 @@ EXPORTS = [
     "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
     "kp_debug_contract",
     "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
+    "kp_complex_fit_create", "kp_complex_fit_steps", "kp_complex_fit_destroy", "kp_complex_fit_error", "kp_complex_fit_launches",
 ]
 
 
@@ -103,6 +104,17 @@ def load_library():
     lib.kp_transe_fit_error.restype = c_char_p
     lib.kp_transe_fit_launches.argtypes = [c_void_p]
     lib.kp_transe_fit_launches.restype = c_int64
+    lib.kp_complex_fit_create.argtypes = [c_int, c_int64, c_int64, c_int32, c_int32, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                          ctypes.c_float, c_int32, c_void_p, c_void_p, POINTER(c_void_p)]
+    lib.kp_complex_fit_create.restype = c_int
+    lib.kp_complex_fit_steps.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.kp_complex_fit_steps.restype = c_int
+    lib.kp_complex_fit_destroy.argtypes = [c_void_p]
+    lib.kp_complex_fit_destroy.restype = c_int
+    lib.kp_complex_fit_error.argtypes = [c_void_p]
+    lib.kp_complex_fit_error.restype = c_char_p
+    lib.kp_complex_fit_launches.argtypes = [c_void_p]
+    lib.kp_complex_fit_launches.restype = c_int64
     _lib = lib
     return lib
 
@@ -347,6 +359,56 @@ class TransEFit:
         if getattr(self, "handle", None):
             torch.cuda.synchronize(self.device)
             self.lib.kp_transe_fit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ComplExFit:
+    """Full-model ComplEx trainer state (kp_complex_fit_*): 1-vs-all cross-entropy + Adagrad / Adam / SGD over the
+    entity and relation tables, CUDA fp32 tensors updated in place (multiclass_nll_optimizer.py:123-135)."""
+
+    OPTIMIZERS = {"Adagrad": 0, "Adam": 1, "SGD": 2}
+
+    def __init__(self, ent, rel, optimizer_name, lr, decay1, decay2, reg_weight, max_batch):
+        self.lib = load_library()
+        if not (ent.is_cuda and rel.is_cuda and ent.is_contiguous() and rel.is_contiguous()
+                and ent.dtype == torch.float32 and rel.dtype == torch.float32):
+            raise RuntimeError("ComplExFit needs contiguous CUDA fp32 tables (kelpie_b200 has no CPU path)")
+        self.ent, self.rel = ent, rel
+        self.device = ent.device
+        h = c_void_p()
+        rc = self.lib.kp_complex_fit_create(ent.device.index or 0, ent.shape[0], rel.shape[0], ent.shape[1],
+                                            self.OPTIMIZERS[optimizer_name], float(lr), float(decay1), float(decay2),
+                                            float(reg_weight), int(max_batch), _ptr(ent), _ptr(rel), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"kp_complex_fit_create failed ({rc}): {self.lib.kp_complex_fit_error(None).decode()}")
+        self.handle = h
+
+    def steps(self, rows, step_off, want_loss=False):
+        """rows: [total, 3] int32 (host or device), permuted; step_off: [n_steps + 1] row offsets (host)."""
+        rows = torch.as_tensor(rows, dtype=torch.int32).to(self.device).contiguous()
+        off = np.ascontiguousarray(step_off, dtype=np.int64)
+        n = len(off) - 1
+        loss = torch.zeros(max(n, 1), dtype=torch.float32, device=self.device) if want_loss else None
+        rc = self.lib.kp_complex_fit_steps(self.handle, n, _np_ptr(off), _ptr(rows), _ptr(loss),
+                                           c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"kp_complex_fit_steps failed ({rc}): {self.lib.kp_complex_fit_error(self.handle).decode()}")
+        self._keep = rows
+        return loss
+
+    def launches(self):
+        return int(self.lib.kp_complex_fit_launches(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.kp_complex_fit_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

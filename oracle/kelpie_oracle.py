@@ -613,3 +613,40 @@ def train_transe_full(ent, rel, norm, training_triples, num_entities, num_relati
             loss.backward()
             opt.step()
     return E.detach().numpy(), R.detach().numpy()
+
+
+def train_complex_full(ent, rel, training_triples, num_relations, hp, n_epochs=None):
+    """Full-model ComplEx training: MultiClassNLLOptimizer.train / epoch / step_on_batch
+    (multiclass_nll_optimizer.py:58-135) with ComplEx.forward (complex.py:58-86), restated with torch autograd on
+    the CPU; consumes the torch CPU generator like the reference (one randperm per epoch)."""
+    E = torch.nn.Parameter(torch.from_numpy(np.array(ent, dtype=np.float32)))
+    R = torch.nn.Parameter(torch.from_numpy(np.array(rel, dtype=np.float32)))
+    name = hp["optimizer_name"]
+    if name == "Adam":
+        opt = torch.optim.Adam([E, R], lr=hp["lr"], betas=(hp["decay1"], hp["decay2"]))
+    else:
+        opt = {"Adagrad": torch.optim.Adagrad, "SGD": torch.optim.SGD}[name]([E, R], lr=hp["lr"])
+    reg = {"N3": _n3, "N2": None}[hp["regularizer_name"]]
+    t = np.asarray(training_triples).astype(np.int64).reshape(-1, 3)
+    inv = t.copy()
+    inv[:, 0], inv[:, 2] = t[:, 2], t[:, 0]
+    inv[:, 1] = t[:, 1] + num_relations
+    rows = torch.from_numpy(np.vstack((t, inv)))
+    d = E.shape[1] // 2
+    bs = min(int(hp["batch_size"]), len(rows))
+    loss_fn = torch.nn.CrossEntropyLoss(reduction="mean")
+    for _ in range(int(n_epochs if n_epochs is not None else hp["epochs"])):
+        perm = rows[torch.randperm(rows.shape[0]), :]
+        b0 = 0
+        while b0 < len(perm):
+            b = perm[b0:min(b0 + bs, len(perm))]
+            lhs, rl, rhs = E[b[:, 0]], R[b[:, 1]], E[b[:, 2]]
+            lhs, rl, rhs = (lhs[:, :d], lhs[:, d:]), (rl[:, :d], rl[:, d:]), (rhs[:, :d], rhs[:, d:])
+            score = (lhs[0] * rl[0] - lhs[1] * rl[1]) @ E[:, :d].t() + (lhs[0] * rl[1] + lhs[1] * rl[0]) @ E[:, d:].t()
+            factors = (torch.sqrt(lhs[0] ** 2 + lhs[1] ** 2), torch.sqrt(rl[0] ** 2 + rl[1] ** 2), torch.sqrt(rhs[0] ** 2 + rhs[1] ** 2))
+            loss = loss_fn(score, b[:, 2]) + reg(factors, float(hp["regularizer_weight"]))
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+            b0 += int(hp["batch_size"])
+    return E.detach().numpy(), R.detach().numpy()

@@ -26,6 +26,9 @@ from src.link_prediction.optimization.pairwise_ranking_optimizer import Pairwise
 
 from tests.golden.make_golden import seed_all, synthetic_kg  # noqa: E402
 
+CX_HP = dict(optimizer_name="Adagrad", batch_size=128, epochs=3, lr=0.043, decay1=0.9, decay2=0.999, regularizer_name="N3",
+             regularizer_weight=0)
+
 HP = dict(batch_size=256, epochs=3, lr=0.01, margin=5, negative_triples_ratio=5, regularizer_weight=1.0)
 
 if __name__ == "__main__":
@@ -46,5 +49,30 @@ if __name__ == "__main__":
         out[f"n{norm}_rel"] = model.relation_embeddings.detach().numpy().copy()
         print("norm", norm, "moved", np.abs(out[f"n{norm}_ent"] - out[f"n{norm}_ent0"]).max())
     path = os.path.join(HERE, "transe_fit_small.npz")
+    np.savez_compressed(path, **out)
+    print("->", path, os.path.getsize(path), "bytes")
+
+    # ---- ComplEx: MultiClassNLLOptimizer.train (Adagrad as in the shipped configs, and Adam)
+    from src.link_prediction.models import ComplEx
+    from src.link_prediction.models.complex import ComplExHyperParams
+    from src.link_prediction.optimization import MultiClassNLLOptimizer
+    from src.link_prediction.optimization.multiclass_nll_optimizer import MultiClassNLLOptimizerHyperParams
+    out = dict(train=train, valid=valid, test=test, n_ent=np.int64(n_ent), n_rel=np.int64(n_rel))
+    for name in ("Adagrad", "Adam"):
+        seed_all(9)
+        model = ComplEx(ds, ComplExHyperParams(dimension=32, init_scale=1e-3), init_random=True)
+        with torch.no_grad():  # the reference's init (scale 1e-3) barely moves in 3 epochs: use a trained-like scale
+            model.entity_embeddings.mul_(300.0)
+            model.relation_embeddings.mul_(300.0)
+        out[f"{name}_ent0"] = model.entity_embeddings.detach().numpy().copy()
+        out[f"{name}_rel0"] = model.relation_embeddings.detach().numpy().copy()
+        seed_all(60)
+        hp = dict(CX_HP, optimizer_name=name, lr=0.043 if name == "Adagrad" else 0.01)
+        opt = MultiClassNLLOptimizer(model=model, hp=MultiClassNLLOptimizerHyperParams(**hp), verbose=False)
+        opt.train(training_triples=ds.training_triples)
+        out[f"{name}_ent"] = model.entity_embeddings.detach().numpy().copy()
+        out[f"{name}_rel"] = model.relation_embeddings.detach().numpy().copy()
+        print(name, "moved", np.abs(out[f"{name}_ent"] - out[f"{name}_ent0"]).max(), "of", np.abs(out[f"{name}_ent0"]).max())
+    path = os.path.join(HERE, "complex_fit_small.npz")
     np.savez_compressed(path, **out)
     print("->", path, os.path.getsize(path), "bytes")

@@ -47,3 +47,32 @@ dt = time.perf_counter() - t0
 out["cpu_port"] = {"steps": k, "us_per_step": 1e6 * dt / k, "steps_per_s": k / dt, "cores": os.cpu_count()}
 out["speedup_steps_per_s"] = out["gpu"]["steps_per_s"] / out["cpu_port"]["steps_per_s"]
 print(json.dumps(out))
+
+# ---- ComplEx (configs/ComplEx_DBpedia50 shape: row 400, batch 512 against all 24 620 entities, Adagrad)
+D = 400
+chp = dict(optimizer_name="Adagrad", batch_size=512, lr=0.043, decay1=0.9, decay2=0.999, regularizer_name="N3", regularizer_weight=0)
+torch.manual_seed(0)
+ent = (torch.randn(N, D) * 0.1).cuda()
+rel = (torch.randn(R2, D) * 0.1).cuda()
+off = np.append(np.arange(0, n, 512), n).astype(np.int64)
+cfit = runtime.ComplExFit(ent, rel, "Adagrad", chp["lr"], 0.9, 0.999, 0, 512)
+perms = [torch.from_numpy(rows[torch.randperm(n).numpy()].astype(np.int32)).cuda() for _ in range(3)]
+cfit.steps(perms[0], off); torch.cuda.synchronize()
+e0.record()
+for p in perms[1:]:
+    cfit.steps(p, off)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+steps = 2 * (len(off) - 1)
+flops = 3 * 2.0 * 512 * N * D  # logits, dQ = P E, gE = P^T Q
+cout = {"shape": {"entities": N, "row": D, "batch": 512, "steps_per_epoch": len(off) - 1},
+        "gpu": {"ms_per_epoch": ms / 2, "us_per_step": 1e3 * ms / steps, "steps_per_s": steps / (ms * 1e-3),
+                "gemm_tflops_alg_if_all_time_were_gemm": flops / (ms / steps * 1e-3) / 1e12}}
+cfit.close()
+k = 6
+t0 = time.perf_counter()
+ko.train_complex_full(ent.cpu().numpy(), rel.cpu().numpy(), ds.training_triples[: k * 256], ds.num_relations, dict(chp, epochs=1), n_epochs=1)
+dt = time.perf_counter() - t0
+cout["cpu_port"] = {"steps": k, "us_per_step": 1e6 * dt / k, "steps_per_s": k / dt, "cores": os.cpu_count()}
+cout["speedup_steps_per_s"] = cout["gpu"]["steps_per_s"] / cout["cpu_port"]["steps_per_s"]
+print(json.dumps({"complex": cout}))
