@@ -21,23 +21,40 @@ def _rows_with_inverses(facts, num_relations):
     return np.vstack((f, inv)) if len(f) else np.zeros((0, 3), dtype=np.int64)
 
 
-def draw_transe(facts, num_relations, n_ent_with_mimic, hp):
-    """pairwise_ranking_optimizer.py:165-195.  Returns (rows_per_epoch, pos [E*n,3], neg [E*n,3])."""
+def draw_transe(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
+    """pairwise_ranking_optimizer.py:165-195.  Returns (rows_per_epoch, pos [E*n,3], neg [E*n,3]).
+
+    Reference order (default): per epoch np.random.shuffle(rows) (cumulative: an index vector is shuffled, which
+    draws the same numbers and applies the same permutation as shuffling the rows), torch.randint(N+1) then
+    torch.randint(2) over ratio * n samples of which the first n are used.  The per-epoch Python work is kept to
+    those three generator calls; the tables are assembled once for all epochs.
+    fast_rng (opt-in, a numpy Generator): independent uniform permutations / corruptions for all epochs in three
+    vectorised draws -- the same distribution, not the reference's random numbers."""
     rows = _rows_with_inverses(facts, num_relations)
     n, E, ratio = len(rows), int(hp["epochs"]), int(hp["negative_triples_ratio"])
-    pos = np.empty((E, n, 3), dtype=np.int32)
-    neg = np.empty((E, n, 3), dtype=np.int32)
+    if n == 0:
+        return 0, np.zeros((0, 3), np.int32), np.zeros((0, 3), np.int32)
     take = np.arange(n) // ratio  # first n rows of np.repeat(rows, ratio)
-    for e in range(E):
-        np.random.shuffle(rows)
-        rnd = torch.randint(high=n_ent_with_mimic, size=(ratio * n,))[:n].numpy()
-        coin = torch.randint(high=2, size=(ratio * n,))[:n].numpy()
-        p = rows[take]
-        pos[e] = p
-        neg[e] = p
-        head = coin == 1
-        neg[e, head, 0] = rnd[head]
-        neg[e, ~head, 2] = rnd[~head]
+    if fast_rng is not None:
+        perm = np.argsort(fast_rng.random((E, n)), axis=1)
+        rnd = fast_rng.integers(0, n_ent_with_mimic, (E, n))
+        coin = fast_rng.integers(0, 2, (E, n))
+    else:
+        perm = np.empty((E, n), dtype=np.int64)
+        rnd_t = torch.empty((E, ratio * n), dtype=torch.int64)
+        coin_t = torch.empty((E, ratio * n), dtype=torch.int64)
+        idx = np.arange(n)
+        for e in range(E):
+            np.random.shuffle(idx)
+            perm[e] = idx
+            torch.randint(n_ent_with_mimic, (ratio * n,), out=rnd_t[e])
+            torch.randint(2, (ratio * n,), out=coin_t[e])
+        rnd, coin = rnd_t.numpy()[:, :n], coin_t.numpy()[:, :n]
+    pos = rows[perm[:, take]].astype(np.int32)  # [E, n, 3]
+    neg = pos.copy()
+    head = coin == 1
+    neg[..., 0] = np.where(head, rnd, pos[..., 0])
+    neg[..., 2] = np.where(head, pos[..., 2], rnd)
     return n, pos.reshape(-1, 3), neg.reshape(-1, 3)
 
 
@@ -58,10 +75,15 @@ def draw_transe_full_epoch(rows, num_entities, ratio):
     return pos, neg
 
 
-def draw_complex(facts, num_relations, hp):
+def draw_complex(facts, num_relations, hp, fast_rng=None):
     """multiclass_nll_optimizer.py:147-164.  Returns (rows_per_epoch, rows, static_epochs)."""
     rows = _rows_with_inverses(facts, num_relations)
     n, E = len(rows), int(hp["epochs"])
+    if fast_rng is not None:
+        if n <= int(hp["batch_size"]):
+            return n, rows.astype(np.int32), True
+        perm = np.argsort(fast_rng.random((E, n)), axis=1)
+        return n, rows[perm].reshape(-1, 3).astype(np.int32), False
     if n <= int(hp["batch_size"]):
         # one step per epoch over ALL rows: the permutation cannot change a mean over the
         # batch, so one epoch of rows is reused; the generator is still advanced as the
@@ -90,8 +112,9 @@ def plan_conve(facts, num_relations):
 class Batch:
     """Accumulates jobs and turns them into the flat arrays of kp_pt_batch."""
 
-    def __init__(self, kind, num_entities, num_relations, hp):
+    def __init__(self, kind, num_entities, num_relations, hp, fast_rng=None):
         self.kind, self.N, self.R, self.hp = kind, int(num_entities), int(num_relations), hp
+        self.fast_rng = fast_rng  # None: the reference's generators in the reference's order
         self.init_rows, self.rows_per_epoch = [], []
         self.pos, self.neg, self.pos_lens, self.pos_ids = [], [], [], []
         self.statics = []
@@ -102,12 +125,12 @@ class Batch:
     def add(self, facts, init_row):
         """Draw (in reference order) and append one job; returns its index in the batch."""
         if self.kind == "TransE":
-            n, pos, neg = draw_transe(facts, self.R, self.N + 1, self.hp)
+            n, pos, neg = draw_transe(facts, self.R, self.N + 1, self.hp, self.fast_rng)
             self.pos.append(pos)
             self.neg.append(neg)
             static = False
         elif self.kind == "ComplEx":
-            n, pos, static = draw_complex(facts, self.R, self.hp)
+            n, pos, static = draw_complex(facts, self.R, self.hp, self.fast_rng)
             self.pos.append(pos)
         else:
             pos, lens, ids = plan_conve(facts, self.R)

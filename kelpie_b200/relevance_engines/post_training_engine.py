@@ -34,6 +34,10 @@ class PostTrainingEngine(RelevanceEngine):
         self.rng_device = "cuda"
         # replay the CPU-generator draws of KelpieConvE's discarded layer initialisers
         self.replay_constructor_rng = True
+        # None (default): shuffles / corruptions / permutations come from the reference's generators in the
+        # reference's order, so the selected explanations are the reference's.  A numpy Generator here draws them
+        # vectorised instead (same distributions, ~30x less host time per TransE candidate).
+        self.fast_rng = None
         self.set_cache()
 
     def set_cache(self):
@@ -84,7 +88,7 @@ class PostTrainingEngine(RelevanceEngine):
         model, kind = self.model, self.model.name
         ctx = context_for(model)
         N, R = self.dataset.num_entities, self.dataset.num_relations
-        batch = plans.Batch(kind, N, R, self.hp)
+        batch = plans.Batch(kind, N, R, self.hp, fast_rng=self.fast_rng)
         job_triple, job_filter = [], []
         pending_base, slots = {}, []
         for pred, rule in items:

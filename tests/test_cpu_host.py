@@ -204,6 +204,37 @@ def test_full_epoch_draw_matches_reference_order():
     assert np.array_equal(pos, rep[:37]) and np.array_equal(neg, want_neg[:37])
 
 
+def test_kelpie_epoch_draws_match_reference_order():
+    """plans.draw_transe = pairwise_ranking_optimizer.py:165-195 over all epochs: np.random.shuffle of the ROWS
+    (cumulative), randint(N+1) then randint(2) over ratio * n samples, first n of the repeated rows used."""
+    import torch
+    from kelpie_b200 import plans
+    rng = np.random.default_rng(1)
+    facts = np.stack([rng.integers(0, 40, 7), rng.integers(0, 3, 7), rng.integers(0, 40, 7)], 1).astype(np.int64)
+    hp = dict(epochs=6, negative_triples_ratio=5)
+    np.random.seed(9); torch.manual_seed(9)
+    n, pos, neg = plans.draw_transe(facts, 3, 41, hp)
+    np.random.seed(9); torch.manual_seed(9)
+    inv = facts[:, [2, 1, 0]].copy(); inv[:, 1] += 3
+    rows = np.vstack((facts, inv))
+    assert n == len(rows) == 14
+    for e in range(6):
+        np.random.shuffle(rows)
+        rep = np.repeat(rows, 5, axis=0)
+        rnd = torch.randint(high=41, size=(len(rep),)).numpy()
+        coin = torch.randint(high=2, size=(len(rep),)).numpy()
+        want = rep.copy()
+        want[coin == 1, 0] = rnd[coin == 1]
+        want[coin != 1, 2] = rnd[coin != 1]
+        assert np.array_equal(pos[e * n:(e + 1) * n], rep[:n]) and np.array_equal(neg[e * n:(e + 1) * n], want[:n])
+    # opt-in vectorised draws: same shapes / value ranges, every epoch a permutation of the rows
+    n2, pos2, neg2 = plans.draw_transe(facts, 3, 41, hp, fast_rng=np.random.default_rng(0))
+    assert n2 == n and pos2.shape == pos.shape and neg2.shape == neg.shape
+    assert set(map(tuple, pos2)) <= set(map(tuple, np.vstack((facts, inv))))
+    changed = (neg2 != pos2)
+    assert not changed[:, 1].any() and not (changed[:, 0] & changed[:, 2]).any() and neg2.max() <= 40
+
+
 def test_dataset_edits_follow_reference_semantics():
     """dataset.py:242-280: add / remove keep train array, per-entity lists, degrees and the DIRECT filter key."""
     from kelpie_b200.data import Dataset

@@ -1,0 +1,57 @@
+"""End-to-end `explain` throughput in the reference's own accounting (#relevances / execution_time,
+stochastic_builder.py:102-107): StochasticBuilder over test predictions of the real DBpedia50 (id-mapped fixture),
+necessary mode, candidates = the head's training facts (the top-20 cut of the topology prefilter for these degrees),
+seeded stand-in weights.  Every host cost is inside the clock: KelpieDataset overlays, plan drawing in the reference's
+RNG order, uploads, kernels, result readback, the builder's control flow.  Prints one JSON line per model."""
+import sys, os, json, time, argparse
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from kelpie_b200.data import Dataset
+from kelpie_b200.link_prediction import MODEL_REGISTRY
+from kelpie_b200.relevance_engines import NecessaryPostTrainingEngine
+from kelpie_b200.explanation_builders import StochasticBuilder
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--preds", type=int, default=20)
+ap.add_argument("--models", default="TransE,ComplEx")
+ap.add_argument("--profile", action="store_true")
+a = ap.parse_args()
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ds = Dataset.from_npz(os.path.join(ROOT, "tests", "golden", "dbpedia50_ids.npz"), name="DBpedia50")
+CFG = {"TransE": (dict(dimension=256, norm=2), dict(batch_size=2048, epochs=65, lr=0.01, margin=5, negative_triples_ratio=5, regularizer_weight=1.0), 0.35),
+       "ComplEx": (dict(dimension=200, init_scale=1e-3), dict(optimizer_name="Adagrad", batch_size=512, epochs=43, lr=0.043, decay1=0.9, decay2=0.999,
+                                                              regularizer_name="N3", regularizer_weight=0), 0.25)}
+preds = []
+for s, p, o in ds.testing_triples:
+    if 3 <= len(ds.entity_to_training_triples[s]) <= 20:
+        preds.append((int(s), int(p), int(o)))
+    if len(preds) == a.preds:
+        break
+for kind in a.models.split(","):
+    params, hp, scale = CFG[kind]
+    cls = MODEL_REGISTRY[kind]["class"]
+    m = cls(ds, cls.get_hyperparams_class()(**params), init_random=False)
+    g = torch.Generator().manual_seed(1)
+    with torch.no_grad():
+        m.entity_embeddings.copy_(torch.randn(m.entity_embeddings.shape, generator=g) * scale)
+        m.relation_embeddings.copy_(torch.randn(m.relation_embeddings.shape, generator=g) * scale)
+    m.eval()
+    eng = NecessaryPostTrainingEngine(m, ds, hp)
+    builder = StochasticBuilder(xsi=5.0, engine=eng, max_explanation_length=4)
+    torch.manual_seed(0); np.random.seed(0)
+    builder.build_explanations(preds[0], ds.entity_to_training_triples[preds[0][0]])  # warm-up: context, split tables
+    torch.cuda.synchronize()
+    if a.profile:
+        import cProfile, pstats
+        pr = cProfile.Profile(); pr.enable()
+    n_rel, t0 = 0, time.perf_counter()
+    for pred in preds:
+        eng.set_cache()
+        out = builder.build_explanations(pred, ds.entity_to_training_triples[pred[0]])
+        n_rel += out["#relevances"]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    if a.profile:
+        pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
+    print(json.dumps({"model": kind, "predictions": len(preds), "relevances": n_rel, "seconds": dt,
+                      "candidates_per_s": n_rel / dt, "ms_per_prediction": 1e3 * dt / len(preds)}))
