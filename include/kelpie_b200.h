@@ -213,6 +213,42 @@ int kp_complex_fit_destroy(kp_cfit* fit);
 const char* kp_complex_fit_error(const kp_cfit* fit); /* fit may be NULL: last create error */
 int64_t kp_complex_fit_launches(const kp_cfit* fit);
 
+/* Full-model ConvE training: BCEOptimizer.step_on_batch (bce_optimizer.py:137-158) with ConvE.forward = all_scores
+ * (conve.py:133-158: batch-norm -> 3x3 conv -> batch-norm -> relu -> Linear -> batch-norm -> relu -> 1-vs-all sigmoid
+ * against the whole entity table), BCELoss(mean) with label smoothing (:104-110) and optim.Adam over EVERY parameter
+ * (:36).  All tensors are DEVICE fp32, contiguous, updated in place (parameters and the batch-norm running statistics).
+ * Batch-norm runs in train mode (batch statistics; running statistics momentum 0.1, unbiased variance) except on a
+ * step of ONE pair, which the reference runs in eval mode (:140-156).  Dropout rates > 0 use counter-based masks
+ * (seed, pair id, step), not torch's Philox stream. */
+typedef struct kp_conve_params {
+  float* ent;      /* [N, dim] */
+  float* rel;      /* [R2, dim] */
+  float* conv_w;   /* [n_filters, 1, 3, 3] */
+  float* conv_b;   /* [n_filters] */
+  float* fc_w;     /* [dim, hidden] */
+  float* fc_b;     /* [dim] */
+  float *bn1_w, *bn1_b, *bn1_mean, *bn1_var; /* [1] each */
+  float *bn2_w, *bn2_b, *bn2_mean, *bn2_var; /* [n_filters] each */
+  float *bn3_w, *bn3_b, *bn3_mean, *bn3_var; /* [dim] each */
+  int32_t n_filters; /* 32 */
+  int32_t hidden;    /* n_filters * 38 * (dim / 20 - 2) */
+  float drop_input, drop_feature, drop_hidden;
+} kp_conve_params;
+typedef struct kp_vfit kp_vfit;
+/* pairs: [n_pairs, 2] int32 (lhs, rel) in er_vocab order (:92-96); pos_off [n_pairs + 1] int64 / pos_ids int32: the
+ * distinct objects of every pair (all three on the DEVICE, kept by the caller for the life of the handle). */
+int kp_conve_fit_create(int device, int64_t n_entities, int64_t n_relations2, int32_t dim, const kp_conve_params* params,
+                        float label_smoothing, int32_t max_batch, int64_t n_pairs, const int32_t* pairs,
+                        const int64_t* pos_off, const int32_t* pos_ids, uint64_t dropout_seed, kp_vfit** out);
+/* n_steps consecutive steps of one epoch at learning rate lr (the caller applies ExponentialLR between epochs, :125-126);
+ * step k trains on pairs order[step_off[k] .. step_off[k+1]) -- order: [n_pairs] int32 (device), this epoch's shuffle;
+ * step_off: host.  loss_out (device, nullable): [n_steps] mean BCE of every step. */
+int kp_conve_fit_steps(kp_vfit* fit, int64_t n_steps, const int64_t* step_off, const int32_t* order, float lr,
+                       float* loss_out, void* stream);
+int kp_conve_fit_destroy(kp_vfit* fit);
+const char* kp_conve_fit_error(const kp_vfit* fit); /* fit may be NULL: last create error */
+int64_t kp_conve_fit_launches(const kp_vfit* fit);
+
 /* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
  * n_rows query vectors [n_rows, D] (device) against the resident entity table:
  *   out_m[g] = max_j z_gj (softmax: the reference max used, >= true max - 8),  out_l[g] = sum_j p_gj,

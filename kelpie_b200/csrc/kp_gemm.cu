@@ -11,7 +11,7 @@ constexpr int GM = 128, GN = 64, GK = 16, GT = 256;
 // C[M,N] = A[M,K] * op(B);  TRANSB: B is [N,K] row-major (C = A B^T), else B is [K,N] row-major
 template <bool TRANSB>
 __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc) {
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, int kb) {
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   const int tid = threadIdx.x;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
     } else {  // B tile from [K,N]: 16 k-rows x 64 cols
       const int k = k0 + (tid >> 4), n = n0 + (tid & 15) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k < K) {
+      if (k < kb) {  // rows of B beyond kb do not exist (A is zero-padded there)
         if (n + 3 < N) {
           v = *reinterpret_cast<const float4*>(B + (size_t)k * ldb + n);
         } else {
@@ -91,15 +91,15 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
 }  // namespace
 
 int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-             int ldc, cudaStream_t st) {
+             int ldc, cudaStream_t st, int k_rows_b) {
   if (M <= 0 || N <= 0) return KP_OK;
   if (K % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "sgemm needs K and leading dimensions multiple of 4");
   dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN);
   KpTimer timer(ctx, kp_ctx::T_CONV, st);
   if (transb)
-    sgemm_kernel<true><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    sgemm_kernel<true><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, K);
   else
-    sgemm_kernel<false><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+    sgemm_kernel<false><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, k_rows_b >= 0 ? k_rows_b : K);
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
 }

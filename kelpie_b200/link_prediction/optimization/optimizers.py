@@ -2,7 +2,7 @@
 (src/link_prediction/optimization/*.py).  Only the Kelpie* subclasses -- the mimic
 post-training -- are on the hot path; they run as ONE job through the batched CUDA kernels
 (the engines batch many).  Of the full-model trainers TransE's and ComplEx's run on the
-device (PairwiseRankingOptimizer.train, MultiClassNLLOptimizer.train); ConvE's stays with the reference.
+device (PairwiseRankingOptimizer.train, MultiClassNLLOptimizer.train, BCEOptimizer.train).
 """
 import numpy as np
 import torch
@@ -198,11 +198,96 @@ class KelpieMultiClassNLLOptimizer(_KelpieOptimizer):
 
 
 class BCEOptimizer(Optimizer):
+    """Full-model ConvE training (bce_optimizer.py:44-158), used by verify_explanations to retrain from scratch: the
+    (s, p) -> objects vocabulary is built once in the reference's order, every epoch's shuffle of the pair list is
+    drawn on the host (np.random.shuffle, the reference's generator), the steps (train-mode batch-norm network, 1-vs-all
+    BCE with label smoothing, Adam over every parameter) run in kp_conve_fit_steps; ExponentialLR is applied between
+    epochs exactly as torch chains it."""
+
     def get_hyperparams_class():
         return BCEOptimizerHyperParams
 
     def get_kelpie_class():
         return KelpieBCEOptimizer
+
+    @staticmethod
+    def er_vocab_tables(rows):
+        """extract_er_vocab (:92-96) as arrays: pairs [P, 2] in first-appearance order, CSR of their DISTINCT objects
+        (targets[rows, cols] = 1.0 is idempotent, :104)."""
+        rows = np.asarray(rows, dtype=np.int64).reshape(-1, 3)
+        key = rows[:, 0] * (int(rows[:, 1].max()) + 1 if len(rows) else 1) + rows[:, 1]
+        uniq, first, inv = np.unique(key, return_index=True, return_inverse=True)
+        rank_of_uniq = np.empty(len(uniq), dtype=np.int64)
+        by_first = np.argsort(first, kind="stable")
+        rank_of_uniq[by_first] = np.arange(len(uniq))
+        pid = rank_of_uniq[inv]  # pair id of every row, pairs numbered by first appearance
+        pairs = rows[first[by_first]][:, :2]
+        po = np.unique(np.stack((pid, rows[:, 2]), 1), axis=0)  # sorted by (pair, object), distinct
+        off = np.zeros(len(pairs) + 1, dtype=np.int64)
+        np.cumsum(np.bincount(po[:, 0], minlength=len(pairs)), out=off[1:])
+        return pairs.astype(np.int32), off, po[:, 1].astype(np.int32)
+
+    def train(self, training_triples, save_path=None, eval_every=-1, valid_triples=None, trial=None, patience=5):
+        hp, model = self.hp, self.model
+        if isinstance(model, KelpieModel):
+            raise Exception("the full-model trainer does not post-train a KelpieModel")
+        if not torch.cuda.is_available():
+            raise RuntimeError("kelpie_b200 has no CPU training path")
+        rows = np.vstack((np.asarray(training_triples), self.dataset.invert_triples(training_triples))).astype(np.int64)
+        pairs, pos_off, pos_ids = self.er_vocab_tables(rows)
+        n, bs = len(pairs), int(hp["batch_size"])
+        model.invalidate_context()  # the scoring context holds copies of the network that is about to change
+        model.cuda()
+        bn1, bn2, bn3 = model.batch_norm_1, model.batch_norm_2, model.batch_norm_3
+        conv, fc = model.convolutional_layer, model.hidden_layer
+        held = dict(ent=model.entity_embeddings, rel=model.relation_embeddings, conv_w=conv.weight, conv_b=conv.bias,
+                    fc_w=fc.weight, fc_b=fc.bias,
+                    bn1_w=bn1.weight, bn1_b=bn1.bias, bn1_mean=bn1.running_mean, bn1_var=bn1.running_var,
+                    bn2_w=bn2.weight, bn2_b=bn2.bias, bn2_mean=bn2.running_mean, bn2_var=bn2.running_var,
+                    bn3_w=bn3.weight, bn3_b=bn3.bias, bn3_mean=bn3.running_mean, bn3_var=bn3.running_var)
+        tensors = {}
+        for k, t in held.items():
+            t.data = t.data.contiguous().float()
+            tensors[k] = t.data
+        fit = runtime.ConvEFit(tensors, model.num_filters, model.hidden_layer_size,
+                               (model.input_dropout_rate, model.feature_map_dropout_rate, model.hidden_dropout_rate),
+                               hp["label_smoothing"], min(bs, n), pairs, pos_off, pos_ids,
+                               seed=int(torch.initial_seed()) & 0xFFFFFFFFFFFF)
+        off = np.append(np.arange(0, n, bs), n).astype(np.int64)
+        order = np.arange(n, dtype=np.int64)
+        lr = float(hp["lr"])
+        best, bad = None, 0
+        self.epoch_losses = []
+        try:
+            for e in range(1, int(hp["epochs"]) + 1):
+                np.random.shuffle(order)  # the same permutation np.random.shuffle applies to the pair list (:114)
+                loss = fit.steps(order.astype(np.int32), off, lr, want_loss=self.verbose)
+                if loss is not None:
+                    self.epoch_losses.append(float(loss.mean()))
+                if hp["decay"]:
+                    lr = lr * float(hp["decay"])  # ExponentialLR.step(): group["lr"] * gamma (:125-126)
+                if valid_triples is not None and eval_every > 0 and e % eval_every == 0:
+                    from ..evaluation import Evaluator
+                    torch.cuda.synchronize()
+                    model.eval()
+                    h1 = Evaluator(model).evaluate(valid_triples)["h1"]
+                    model.invalidate_context()
+                    if trial is not None:
+                        trial.report(h1, e)
+                        if trial.should_prune():
+                            raise RuntimeError("trial pruned")
+                    if best is None or h1 > best:
+                        best, bad = h1, 0
+                    else:
+                        bad += 1
+                    if bad >= patience:
+                        break
+            self.launches = fit.launches()
+        finally:
+            fit.close()
+        model.invalidate_context()
+        if save_path is not None:
+            torch.save(model.state_dict(), save_path)
 
 
 class KelpieBCEOptimizer(_KelpieOptimizer):

@@ -24,6 +24,7 @@ EXPORTS = [
     "kp_debug_contract",
     "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
     "kp_complex_fit_create", "kp_complex_fit_steps", "kp_complex_fit_destroy", "kp_complex_fit_error", "kp_complex_fit_launches",
+    "kp_conve_fit_create", "kp_conve_fit_steps", "kp_conve_fit_destroy", "kp_conve_fit_error", "kp_conve_fit_launches",
 ]
 
 
@@ -115,6 +116,17 @@ def load_library():
     lib.kp_complex_fit_error.restype = c_char_p
     lib.kp_complex_fit_launches.argtypes = [c_void_p]
     lib.kp_complex_fit_launches.restype = c_int64
+    lib.kp_conve_fit_create.argtypes = [c_int, c_int64, c_int64, c_int32, POINTER(ConvEParams), ctypes.c_float, c_int32, c_int64,
+                                        c_void_p, c_void_p, c_void_p, ctypes.c_uint64, POINTER(c_void_p)]
+    lib.kp_conve_fit_create.restype = c_int
+    lib.kp_conve_fit_steps.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, ctypes.c_float, c_void_p, c_void_p]
+    lib.kp_conve_fit_steps.restype = c_int
+    lib.kp_conve_fit_destroy.argtypes = [c_void_p]
+    lib.kp_conve_fit_destroy.restype = c_int
+    lib.kp_conve_fit_error.argtypes = [c_void_p]
+    lib.kp_conve_fit_error.restype = c_char_p
+    lib.kp_conve_fit_launches.argtypes = [c_void_p]
+    lib.kp_conve_fit_launches.restype = c_int64
     _lib = lib
     return lib
 
@@ -409,6 +421,70 @@ class ComplExFit:
         if getattr(self, "handle", None):
             torch.cuda.synchronize(self.device)
             self.lib.kp_complex_fit_destroy(self.handle)
+            self.handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class ConvEParams(ctypes.Structure):
+    """kp_conve_params (include/kelpie_b200.h): device pointers of every trainable tensor + batch-norm running statistics."""
+    _fields_ = [(n, c_void_p) for n in ("ent", "rel", "conv_w", "conv_b", "fc_w", "fc_b",
+                                         "bn1_w", "bn1_b", "bn1_mean", "bn1_var", "bn2_w", "bn2_b", "bn2_mean", "bn2_var",
+                                         "bn3_w", "bn3_b", "bn3_mean", "bn3_var")] + [
+        ("n_filters", c_int32), ("hidden", c_int32),
+        ("drop_input", ctypes.c_float), ("drop_feature", ctypes.c_float), ("drop_hidden", ctypes.c_float)]
+
+
+class ConvEFit:
+    """Full-model ConvE trainer state (kp_conve_fit_*): 1-vs-all BCE with label smoothing + Adam over every parameter of
+    the network, CUDA fp32 tensors updated in place (bce_optimizer.py:137-158, conve.py:133-158)."""
+
+    def __init__(self, tensors, n_filters, hidden, dropouts, label_smoothing, max_batch, pairs, pos_off, pos_ids, seed=0):
+        self.lib = load_library()
+        for k, t in tensors.items():
+            if not (t.is_cuda and t.is_contiguous() and t.dtype == torch.float32):
+                raise RuntimeError(f"ConvEFit needs contiguous CUDA fp32 tensors ({k}); kelpie_b200 has no CPU path")
+        self.tensors = tensors
+        ent, rel = tensors["ent"], tensors["rel"]
+        self.device = ent.device
+        prm = ConvEParams(n_filters=int(n_filters), hidden=int(hidden), drop_input=float(dropouts[0]),
+                          drop_feature=float(dropouts[1]), drop_hidden=float(dropouts[2]),
+                          **{k: t.data_ptr() for k, t in tensors.items()})
+        self.pairs = torch.as_tensor(np.ascontiguousarray(pairs, dtype=np.int32)).to(self.device)
+        self.pos_off = torch.as_tensor(np.ascontiguousarray(pos_off, dtype=np.int64)).to(self.device)
+        self.pos_ids = torch.as_tensor(np.ascontiguousarray(pos_ids, dtype=np.int32)).to(self.device)
+        h = c_void_p()
+        rc = self.lib.kp_conve_fit_create(ent.device.index or 0, ent.shape[0], rel.shape[0], ent.shape[1], ctypes.byref(prm),
+                                          float(label_smoothing), int(max_batch), len(self.pairs), _ptr(self.pairs),
+                                          _ptr(self.pos_off), _ptr(self.pos_ids), int(seed), ctypes.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"kp_conve_fit_create failed ({rc}): {self.lib.kp_conve_fit_error(None).decode()}")
+        self.handle = h
+
+    def steps(self, order, step_off, lr, want_loss=False):
+        """order: [n_pairs] int32, this epoch's shuffle of the pair table; step_off: [n_steps + 1] offsets into it (host)."""
+        order = torch.as_tensor(np.ascontiguousarray(order, dtype=np.int32)).to(self.device)
+        off = np.ascontiguousarray(step_off, dtype=np.int64)
+        n = len(off) - 1
+        loss = torch.zeros(max(n, 1), dtype=torch.float32, device=self.device) if want_loss else None
+        rc = self.lib.kp_conve_fit_steps(self.handle, n, _np_ptr(off), _ptr(order), float(lr), _ptr(loss),
+                                         c_void_p(torch.cuda.current_stream(self.device).cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"kp_conve_fit_steps failed ({rc}): {self.lib.kp_conve_fit_error(self.handle).decode()}")
+        self._keep = order
+        return loss
+
+    def launches(self):
+        return int(self.lib.kp_conve_fit_launches(self.handle))
+
+    def close(self):
+        if getattr(self, "handle", None):
+            torch.cuda.synchronize(self.device)
+            self.lib.kp_conve_fit_destroy(self.handle)
             self.handle = None
 
     def __del__(self):

@@ -650,3 +650,73 @@ def train_complex_full(ent, rel, training_triples, num_relations, hp, n_epochs=N
             opt.step()
             b0 += int(hp["batch_size"])
     return E.detach().numpy(), R.detach().numpy()
+
+
+CONVE_STATE_KEYS = ("entity_embeddings", "relation_embeddings", "batch_norm_1.weight", "batch_norm_1.bias",
+                    "batch_norm_1.running_mean", "batch_norm_1.running_var", "batch_norm_2.weight", "batch_norm_2.bias",
+                    "batch_norm_2.running_mean", "batch_norm_2.running_var", "batch_norm_3.weight", "batch_norm_3.bias",
+                    "batch_norm_3.running_mean", "batch_norm_3.running_var", "convolutional_layer.weight",
+                    "convolutional_layer.bias", "hidden_layer.weight", "hidden_layer.bias")
+
+
+def train_conve_full(state, training_triples, num_entities, num_relations, hp, n_epochs=None, max_steps=None, dtype=np.float32):
+    """Full-model ConvE training: BCEOptimizer.train / epoch / extract_batch / step_on_batch (bce_optimizer.py:44-158)
+    with ConvE.forward = all_scores (conve.py:133-158), restated with torch autograd on the CPU (dropout rates 0).
+    `state`: dict of arrays under the reference's state-dict keys (CONVE_STATE_KEYS); returns the trained dict.
+    Quirks kept: pairs (s, p) in first-appearance order over triples + inverses, np.random.shuffle of the PAIR LIST
+    per epoch (cumulative), multi-hot targets * (1 - ls) + 1 / N, batch-norm in train mode (batch statistics, running
+    statistics with momentum 0.1 and the unbiased variance) except on a step of ONE pair (:140-156), Adam over every
+    parameter, ExponentialLR stepped per epoch when decay != 0 (:125-126)."""
+    P = {k: torch.nn.Parameter(torch.from_numpy(np.array(state[k], dtype=dtype))) for k in CONVE_STATE_KEYS
+         if "running" not in k}
+    S = {k: torch.from_numpy(np.array(state[k], dtype=dtype)) for k in CONVE_STATE_KEYS if "running" in k}
+    opt = torch.optim.Adam(list(P.values()), lr=hp["lr"])
+    sched = torch.optim.lr_scheduler.ExponentialLR(opt, hp["decay"])
+    t = np.asarray(training_triples).astype(np.int64).reshape(-1, 3)
+    inv = t.copy()
+    inv[:, 0], inv[:, 2] = t[:, 2], t[:, 0]
+    inv[:, 1] = t[:, 1] + num_relations
+    vocab = {}
+    for s, p, o in np.vstack((t, inv)):
+        vocab.setdefault((s, p), []).append(o)
+    pairs = list(vocab.keys())
+    bs, ls, N = int(hp["batch_size"]), float(hp["label_smoothing"]), int(num_entities)
+    D = P["entity_embeddings"].shape[1]
+    loss_fn = torch.nn.BCELoss()
+
+    def bn(x, name, train):
+        return F.batch_norm(x, S[name + ".running_mean"], S[name + ".running_var"], P[name + ".weight"], P[name + ".bias"],
+                            train, 0.1, 1e-5)
+
+    done = 0
+    for _ in range(int(n_epochs if n_epochs is not None else hp["epochs"])):
+        np.random.shuffle(pairs)
+        for b0 in range(0, len(pairs), bs):
+            if max_steps is not None and done >= max_steps:  # diagnostic: stop after a number of steps
+                break
+            done += 1
+            batch = pairs[b0:b0 + bs]
+            targets = torch.zeros((len(batch), N), dtype=P["entity_embeddings"].dtype)
+            for i, pr in enumerate(batch):
+                targets[i, vocab[pr]] = 1.0
+            if ls:
+                targets = (1.0 - ls) * targets + 1.0 / N
+            idx = torch.tensor(batch)
+            train = len(batch) > 1
+            lhs = P["entity_embeddings"][idx[:, 0]].view(-1, 1, 20, D // 20)
+            rel = P["relation_embeddings"][idx[:, 1]].view(-1, 1, 20, D // 20)
+            x = bn(torch.cat([lhs, rel], 2), "batch_norm_1", train)
+            x = F.conv2d(x, P["convolutional_layer.weight"], P["convolutional_layer.bias"])
+            x = torch.relu(bn(x, "batch_norm_2", train)).view(len(batch), -1)
+            x = F.linear(x, P["hidden_layer.weight"], P["hidden_layer.bias"])
+            x = torch.relu(bn(x, "batch_norm_3", train))
+            pred = torch.sigmoid(x @ P["entity_embeddings"].t())
+            loss = loss_fn(pred, targets)
+            opt.zero_grad()
+            loss.backward()
+            opt.step()
+        if hp["decay"]:
+            sched.step()
+    out = {k: v.detach().numpy() for k, v in P.items()}
+    out.update({k: v.numpy() for k, v in S.items()})
+    return out
