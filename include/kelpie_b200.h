@@ -149,6 +149,14 @@ int kp_filter_upload(kp_ctx* ctx, int64_t n_keys, const int64_t* keys, const int
 
 /* ---- scoring / ranking --------------------------------------------------------------- */
 
+/* Device builder of the same CSR: replaces the host walk over the dict Dataset.to_filter
+ * (dataset.py:131-139).  facts: [n_facts, 3] int32 rows (entity, relation, id) = "id is a known answer of
+ * (entity, relation)", host or device, any order, duplicates allowed (the dict holds multiset lists).  Sort + unique +
+ * segment on the device; the resident CSR is identical to what kp_filter_upload receives from the dict walk.
+ * Needs N * R2 < 2^31.  kp_filter_download reads the resident CSR back (call with NULL arrays for the sizes). */
+int kp_filter_build(kp_ctx* ctx, int64_t n_facts, const int32_t* facts, void* stream);
+int kp_filter_download(kp_ctx* ctx, int64_t* n_keys, int64_t* n_ids, int64_t* keys, int64_t* offsets, int32_t* ids);
+
 /* Model.all_scores (transe.py:48-65, complex.py:88-113, conve.py:133-158):
  * out[q, j] = score of (s_q, p_q, j), row stride out_ld floats, N (+1) columns. */
 int kp_all_scores(kp_ctx* ctx, int32_t n_queries, const int32_t* triples,

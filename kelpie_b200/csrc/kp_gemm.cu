@@ -11,7 +11,8 @@ constexpr int GM = 128, GN = 64, GK = 16, GT = 256;
 // C[M,N] = A[M,K] * op(B);  TRANSB: B is [N,K] row-major (C = A B^T), else B is [K,N] row-major
 template <bool TRANSB>
 __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
-                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, int kb) {
+                                                   const float* __restrict__ B, int ldb, float* __restrict__ C, int ldc, int kb,
+                                                   int k_per_split) {
   __shared__ float As[GK][GM + 4];
   __shared__ float Bs[GK][GN + 4];
   const int tid = threadIdx.x;
@@ -24,7 +25,9 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int a_row = tid >> 1, a_k = (tid & 1) * 8;
-  for (int k0 = 0; k0 < K; k0 += GK) {
+  const int k_begin = k_per_split > 0 ? (int)blockIdx.z * k_per_split : 0;
+  if (k_per_split > 0) K = min(K, k_begin + k_per_split);  // split-K: this CTA's range (a multiple of GK long)
+  for (int k0 = k_begin; k0 < K; k0 += GK) {
     {  // A tile: [128 rows x 16 k], stored transposed
       const int m = m0 + a_row;
 #pragma unroll
@@ -83,7 +86,10 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int n = n0 + tx * 4 + j;
-      if (n < N) C[(size_t)m * ldc + n] = acc[i][j];
+      if (n < N) {
+        if (k_per_split > 0) atomicAdd(C + (size_t)m * ldc + n, acc[i][j]);
+        else C[(size_t)m * ldc + n] = acc[i][j];
+      }
     }
   }
 }
@@ -95,11 +101,23 @@ int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int 
   if (M <= 0 || N <= 0) return KP_OK;
   if (K % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "sgemm needs K and leading dimensions multiple of 4");
   dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN);
+  // few output tiles and a long K: cut K over blockIdx.z (partial sums reduced with fp32 atomics into a zeroed C)
+  int k_per_split = 0;
+  const long long tiles = (long long)grid.x * grid.y;
+  if (tiles * 2 <= ctx->sm_count && K >= 64 * GK) {
+    int splits = (int)((2LL * ctx->sm_count + tiles - 1) / tiles);
+    if (splits > K / (8 * GK)) splits = K / (8 * GK);
+    if (splits > 1) {
+      k_per_split = ((K + splits - 1) / splits + GK - 1) / GK * GK;
+      grid.z = (K + k_per_split - 1) / k_per_split;
+      KP_CUDA(ctx, cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)N * 4, (size_t)M, st));
+    }
+  }
   KpTimer timer(ctx, kp_ctx::T_CONV, st);
   if (transb)
-    sgemm_kernel<true><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, K);
+    sgemm_kernel<true><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, K, k_per_split);
   else
-    sgemm_kernel<false><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, k_rows_b >= 0 ? k_rows_b : K);
+    sgemm_kernel<false><<<grid, GT, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc, k_rows_b >= 0 ? k_rows_b : K, k_per_split);
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
 }

@@ -75,6 +75,10 @@ class Dataset:
         for s, p, o in self.all_triples:
             self.to_filter[(s, p)].append(o)
             self.to_filter[(o, p + R)].append(s)
+        # the same multiset as rows (entity, relation, id) for the device CSR builder (kp_filter_build); edits are logged
+        a = np.asarray(self.all_triples, dtype=np.int64).reshape(-1, 3)
+        self._filter_base = np.vstack((a, np.stack((a[:, 2], a[:, 1] + R, a[:, 0]), 1))).astype(np.int32)
+        self._filter_added, self._filter_removed = [], []
         self._compute_relation_to_type()
 
     # -- attributes of the reference class ------------------------------------------------
@@ -149,6 +153,7 @@ class Dataset:
         self.entity_to_degree[o] = self.entity_to_degree.get(o, 0) + 1
         self.to_filter[(s, p)].append(o)  # like the reference, only the direct key is maintained
         self.train_to_filter[(s, p)].append(o)
+        self._filter_added.append((s, p, o))
 
     def add_training_triples(self, triples):
         for t in triples:
@@ -166,10 +171,26 @@ class Dataset:
             self.entity_to_degree[o] -= 1
         self.to_filter[(s, p)].remove(o)
         self.train_to_filter[(s, p)].remove(o)
+        self._filter_removed.append((s, p, o))
 
     def remove_training_triples(self, triples):
         for t in set(tuple(int(x) for x in t) for t in triples):
             self.remove_training_triple(t)
+
+    def filter_facts(self):
+        """The multiset `to_filter` as int32 rows (entity, relation, id) -- input of the device CSR builder
+        (runtime.Context.build_filter / kp_filter_build).  Edits follow the dict: an added training fact contributes its
+        DIRECT key only, a removed one takes away ONE occurrence of its direct row (dataset.py:242-280)."""
+        rows = self._filter_base
+        if self._filter_added:
+            rows = np.vstack((rows, np.asarray(self._filter_added, dtype=np.int32)))
+        if self._filter_removed:
+            keep = np.ones(len(rows), dtype=bool)
+            for s, p, o in self._filter_removed:
+                hit = np.flatnonzero(keep & (rows[:, 0] == s) & (rows[:, 1] == p) & (rows[:, 2] == o))
+                keep[hit[0]] = False  # list.remove: first occurrence; which copy goes does not matter to a multiset
+            rows = rows[keep]
+        return np.ascontiguousarray(rows, dtype=np.int32)
 
     def invert_triples(self, triples):
         """dataset.py:319-331."""

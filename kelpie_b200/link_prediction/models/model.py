@@ -32,7 +32,11 @@ def context_for(model):
     if ctx is None:
         w = model_weights(model)
         ctx = runtime.Context(w["kind"], w["ent"], w["rel"], norm=w["norm"], conve=w["conve"])
-        ctx.upload_filter(model.dataset.to_filter)
+        ds = model.dataset
+        if hasattr(ds, "filter_facts") and ctx.N * ctx.R2 < 2 ** 31:
+            ctx.build_filter(ds.filter_facts())  # sort / unique / segment on the device (kp_filter_build)
+        else:
+            ctx.upload_filter(ds.to_filter)
         object.__setattr__(model, "_kp_ctx", ctx)
     return ctx
 

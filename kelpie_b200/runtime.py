@@ -20,6 +20,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkelpie_
 
 EXPORTS = [
     "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
+    "kp_filter_build", "kp_filter_download",
     "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
     "kp_debug_contract",
     "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
@@ -79,6 +80,10 @@ def load_library():
     lib.kp_abi_version.restype = c_int
     lib.kp_filter_upload.argtypes = [c_void_p, c_int64, c_void_p, c_void_p, c_void_p]
     lib.kp_filter_upload.restype = c_int
+    lib.kp_filter_build.argtypes = [c_void_p, c_int64, c_void_p, c_void_p]
+    lib.kp_filter_build.restype = c_int
+    lib.kp_filter_download.argtypes = [c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, c_void_p, c_void_p]
+    lib.kp_filter_download.restype = c_int
     lib.kp_all_scores.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     lib.kp_all_scores.restype = c_int
     lib.kp_filtered_rank.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
@@ -233,6 +238,21 @@ class Context:
         self._check(self.lib.kp_filter_upload(self.handle, len(keys), _np_ptr(keys), _np_ptr(off), _np_ptr(ids)),
                     "kp_filter_upload")
         self.has_filter = True
+
+    def build_filter(self, facts):
+        """facts: [F, 3] int32 rows (entity, relation, id) (Dataset.filter_facts()); the CSR is built on the device."""
+        facts = np.ascontiguousarray(facts, dtype=np.int32).reshape(-1, 3)
+        self._check(self.lib.kp_filter_build(self.handle, len(facts), _np_ptr(facts), self._stream()), "kp_filter_build")
+        self.has_filter = True
+
+    def download_filter(self):
+        """(keys, offsets, ids) of the resident CSR as numpy arrays."""
+        nk, ni = c_int64(), c_int64()
+        self._check(self.lib.kp_filter_download(self.handle, ctypes.byref(nk), ctypes.byref(ni), None, None, None), "kp_filter_download")
+        keys, off, ids = np.zeros(nk.value, np.int64), np.zeros(nk.value + 1, np.int64), np.zeros(ni.value, np.int32)
+        self._check(self.lib.kp_filter_download(self.handle, ctypes.byref(nk), ctypes.byref(ni), _np_ptr(keys), _np_ptr(off),
+                                                _np_ptr(ids)), "kp_filter_download")
+        return keys, off, ids
 
     def all_scores(self, triples, mimic_rows=None):
         """[Q,3] int triples -> [Q, N(+1)] fp32 device tensor."""

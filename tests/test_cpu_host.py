@@ -249,3 +249,32 @@ def test_dataset_edits_follow_reference_semantics():
     assert (2, 0, 3) in ds.entity_to_training_triples[3] and ds.entity_to_degree[3] == 2
     with pytest.raises(ValueError):
         ds.remove_training_triple((1, 0, 0))           # like list.remove in the reference
+
+
+def test_filter_facts_equal_the_to_filter_dict_after_edits():
+    """Dataset.filter_facts() (input of the device CSR builder) carries the same multiset as the dict
+    Dataset.to_filter (dataset.py:131-139), including the reference's edit quirks: an added fact only gets its direct
+    key, a removed one loses one occurrence of its direct row while a copy in valid / test keeps it filtered."""
+    from kelpie_b200 import runtime
+    from kelpie_b200.data import Dataset
+    rng = np.random.default_rng(3)
+    tr = np.stack([rng.integers(0, 40, 300), rng.integers(0, 5, 300), rng.integers(0, 40, 300)], 1)
+    te = np.vstack((tr[:20], np.stack([rng.integers(0, 40, 30), rng.integers(0, 5, 30), rng.integers(0, 40, 30)], 1)))
+    ds = Dataset("t", tr, tr[20:30], te, 40, 5)
+
+    def csr_of_facts(rows):
+        u = np.unique(np.stack((rows[:, 0].astype(np.int64) * 10 + rows[:, 1], rows[:, 2]), 1), axis=0)
+        keys, counts = np.unique(u[:, 0], return_counts=True)
+        return keys, np.concatenate(([0], np.cumsum(counts))), u[:, 1].astype(np.int32)
+
+    def same():
+        a, b = csr_of_facts(ds.filter_facts()), runtime.filter_csr(ds.to_filter, 10)
+        return all(np.array_equal(x, y) for x, y in zip(a, b))
+
+    assert same()
+    ds.remove_training_triples([tuple(tr[0]), tuple(tr[25]), tuple(tr[100])])  # tr[0] also in test, tr[25] also in valid
+    assert same()
+    ds.add_training_triples([(1, 2, 3), (39, 4, 0), (1, 2, 3)])
+    assert same()
+    ds.remove_training_triple((1, 2, 3))
+    assert same()

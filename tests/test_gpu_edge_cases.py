@@ -178,3 +178,29 @@ def test_streaming_pass_equals_tile_pass(kind, Q):
     np.testing.assert_array_equal(res[0][1][2], res[1][1][2])   # ranks
     np.testing.assert_array_equal(res[0][1][3], res[1][1][3])   # counters
     np.testing.assert_allclose(res[0][1][0], res[1][1][0], rtol=2e-5, atol=1e-6)
+
+
+@pytest.mark.gpu
+def test_device_built_filter_csr_equals_dict_upload():
+    """kp_filter_build (sort / unique / segment on the device) leaves the same resident CSR as
+    kp_filter_upload fed by the dict walk -- on the real DBpedia50 filter (train + valid + test, both directions),
+    after dataset edits, and for the empty case."""
+    import os
+    from kelpie_b200 import runtime
+    from kelpie_b200.data import Dataset
+    from tests.golden_util import GOLDEN
+    ds = Dataset.from_npz(os.path.join(GOLDEN, "dbpedia50_ids.npz"), name="DBpedia50")
+    ds.remove_training_triples([tuple(int(x) for x in t) for t in ds.training_triples[:50]])
+    ds.add_training_triples([(5, 3, 9), (5, 3, 9), (17, 0, 2)])
+    N, R2 = ds.num_entities, 2 * ds.num_relations
+    ent, rel = torch.zeros(N, 8), torch.zeros(R2, 8)
+    a, b = runtime.Context("TransE", ent, rel), runtime.Context("TransE", ent, rel)
+    a.upload_filter(ds.to_filter)
+    b.build_filter(ds.filter_facts())
+    for x, y in zip(a.download_filter(), b.download_filter()):
+        assert x.dtype == y.dtype and np.array_equal(x, y)
+    keys, off, ids = b.download_filter()
+    assert len(keys) > 30000 and (np.diff(keys) > 0).all() and off[-1] == len(ids)
+    b.build_filter(np.zeros((0, 3), np.int32))
+    assert [len(x) for x in b.download_filter()] == [0, 1, 0]
+    a.close(); b.close()

@@ -76,3 +76,34 @@ dt = time.perf_counter() - t0
 cout["cpu_port"] = {"steps": k, "us_per_step": 1e6 * dt / k, "steps_per_s": k / dt, "cores": os.cpu_count()}
 cout["speedup_steps_per_s"] = cout["gpu"]["steps_per_s"] / cout["cpu_port"]["steps_per_s"]
 print(json.dumps({"complex": cout}))
+
+# ---- ConvE (configs/ConvE_DBpedia50 shape: dimension 200, hidden 9728, batch 512 pairs against all 24 620 entities, Adam)
+from kelpie_b200.link_prediction import MODEL_REGISTRY
+cls, opt_cls = MODEL_REGISTRY["ConvE"]["class"], MODEL_REGISTRY["ConvE"]["optimizer"]
+torch.manual_seed(0); np.random.seed(0)
+m = cls(ds, cls.get_hyperparams_class()(dimension=200, input_dropout_rate=0.0, feature_map_dropout_rate=0.0, hidden_dropout_rate=0.0,
+                                        hidden_layer_size=9728), init_random=True)
+vhp = dict(batch_size=512, label_smoothing=0.1, lr=0.018, decay=0.995, epochs=3)
+opt = opt_cls(model=m, hp=opt_cls.get_hyperparams_class()(**vhp), verbose=False)
+pairs, _, _ = opt_cls.er_vocab_tables(rows)
+spe = -(-len(pairs) // 512)
+opt.hp["epochs"] = 1
+opt.train(training_triples=ds.training_triples); torch.cuda.synchronize()   # warm-up epoch (allocations, workspace growth)
+opt.hp["epochs"] = 2
+e0.record()
+opt.train(training_triples=ds.training_triples)
+e1.record(); torch.cuda.synchronize()
+ms = e0.elapsed_time(e1)
+steps = 2 * spe
+flops = 2.0 * 512 * (3 * N * 200 + 3 * 200 * 9728)  # Z, dX, gE against the table; H, gW, dfeat through the Linear layer
+vout = {"shape": {"entities": N, "dim": 200, "hidden": 9728, "batch": 512, "pairs": int(len(pairs)), "steps_per_epoch": spe},
+        "gpu": {"ms_per_epoch": ms / 2, "us_per_step": 1e3 * ms / steps, "steps_per_s": steps / (ms * 1e-3),
+                "gemm_tflops_alg_if_all_time_were_gemm": flops / (ms / steps * 1e-3) / 1e12, "includes": "host er_vocab + per-epoch shuffle upload"}}
+state = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items() if "num_batches" not in k}
+k = 4
+t0 = time.perf_counter()
+ko.train_conve_full(state, ds.training_triples, N, ds.num_relations, vhp, n_epochs=1, max_steps=k)
+dt = time.perf_counter() - t0
+vout["cpu_port"] = {"steps": k, "us_per_step": 1e6 * dt / k, "steps_per_s": k / dt, "cores": os.cpu_count(), "includes": "er_vocab construction"}
+vout["speedup_steps_per_s"] = vout["gpu"]["steps_per_s"] / vout["cpu_port"]["steps_per_s"]
+print(json.dumps({"conve": vout}))

@@ -11,7 +11,7 @@ from kelpie_b200 import runtime
 
 z = np.load(os.path.join(GOLDEN, "conve_fit_small.npz"))
 MODEL_HP = dict(dimension=60, input_dropout_rate=0.0, feature_map_dropout_rate=0.0, hidden_dropout_rate=0.0, hidden_layer_size=1216)
-HP = dict(batch_size=int(sys.argv[1]) if len(sys.argv) > 1 else 128, label_smoothing=0.1, lr=0.003, decay=0.995, epochs=1)
+HP = dict(batch_size=int(sys.argv[1]) if len(sys.argv) > 1 else 128, label_smoothing=0.1, lr=0.003, decay=0.995, epochs=3)
 ds = Dataset("golden-fit", z["train"], z["valid"], z["test"], int(z["n_ent"]), int(z["n_rel"]))
 cls, opt_cls = MODEL_REGISTRY["ConvE"]["class"], MODEL_REGISTRY["ConvE"]["optimizer"]
 state = {k: z["init/" + k] for k in ko.CONVE_STATE_KEYS}
@@ -23,8 +23,11 @@ for n_steps in [int(x) for x in (sys.argv[2].split(',') if len(sys.argv) > 2 els
     seed_all(70)
     opt = opt_cls(model=m, hp=opt_cls.get_hyperparams_class()(**HP), verbose=True)
     orig = runtime.ConvEFit.steps
-    def limited(self, order, off, lr, want_loss=False, _n=n_steps):
-        return orig(self, order, off[:_n + 1], lr, want_loss)
+    budget = [n_steps]
+    def limited(self, order, off, lr, want_loss=False):
+        n = min(budget[0], len(off) - 1)
+        budget[0] -= n
+        return orig(self, order, off[:n + 1], lr, want_loss)
     runtime.ConvEFit.steps = limited
     opt.train(training_triples=ds.training_triples)
     runtime.ConvEFit.steps = orig
