@@ -257,6 +257,14 @@ int kp_conve_fit_destroy(kp_vfit* fit);
 const char* kp_conve_fit_error(const kp_vfit* fit); /* fit may be NULL: last create error */
 int64_t kp_conve_fit_launches(const kp_vfit* fit);
 
+/* Data-poisoning baseline (data_poisoning_engine.py:21-141) for ComplEx: per job (prediction, training fact,
+ * perspective entity in {pred.s, pred.o}) the relevance of the fact = change of its score when the entity's embedding
+ * moves by epsilon along -/+ the gradient of the prediction's score (necessary / sufficient).  preds / facts: [n, 3]
+ * int32, entity: [n] int32, out: [n] fp32 -- all on the device.  Other model kinds: KP_EUNSUPPORTED (the reference's
+ * engine calls Model.score_embeddings, which TransE and ConvE do not define). */
+int kp_dp_relevance(kp_ctx* ctx, int32_t n_jobs, const int32_t* preds, const int32_t* facts, const int32_t* entity,
+                    float epsilon, float lambd, int32_t sufficient, float* out, void* stream);
+
 /* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
  * n_rows query vectors [n_rows, D] (device) against the resident entity table:
  *   out_m[g] = max_j z_gj (softmax: the reference max used, >= true max - 8),  out_l[g] = sum_j p_gj,

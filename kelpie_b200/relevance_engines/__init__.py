@@ -4,3 +4,4 @@ from .post_training_engine import (
     NecessaryPostTrainingEngine,
     SufficientPostTrainingEngine,
 )
+from .data_poisoning_engine import DPEngine, NecessaryDPEngine, SufficientDPEngine

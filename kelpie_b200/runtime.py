@@ -22,7 +22,7 @@ EXPORTS = [
     "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
     "kp_filter_build", "kp_filter_download",
     "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
-    "kp_debug_contract",
+    "kp_debug_contract", "kp_dp_relevance",
     "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
     "kp_complex_fit_create", "kp_complex_fit_steps", "kp_complex_fit_destroy", "kp_complex_fit_error", "kp_complex_fit_launches",
     "kp_conve_fit_create", "kp_conve_fit_steps", "kp_conve_fit_destroy", "kp_conve_fit_error", "kp_conve_fit_launches",
@@ -99,6 +99,9 @@ def load_library():
     lib.kp_stat.restype = c_int
     lib.kp_debug_contract.argtypes = [c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.kp_debug_contract.restype = c_int
+    lib.kp_dp_relevance.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, ctypes.c_float, ctypes.c_float, c_int32,
+                                    c_void_p, c_void_p]
+    lib.kp_dp_relevance.restype = c_int
     lib.kp_transe_fit_create.argtypes = [c_int, c_int64, c_int64, c_int32, c_int32, ctypes.c_float, ctypes.c_float,
                                          ctypes.c_float, c_void_p, c_void_p, POINTER(c_void_p)]
     lib.kp_transe_fit_create.restype = c_int
@@ -282,6 +285,16 @@ class Context:
                                               _ptr(ts), _ptr(bs), _ptr(rk), _ptr(cn), self._stream()),
                     "kp_filtered_rank")
         return (ts, bs, rk, cn) if counters else (ts, bs, rk)
+
+    def dp_relevance(self, preds, facts, entities, epsilon, lambd=1.0, sufficient=False):
+        """Data-poisoning relevances (kp_dp_relevance): [n] fp32 device tensor."""
+        p = self.dev(preds, torch.int32).view(-1, 3)
+        f = self.dev(facts, torch.int32).view(-1, 3)
+        e = self.dev(entities, torch.int32).view(-1)
+        out = torch.empty(p.shape[0], dtype=torch.float32, device=self.device)
+        self._check(self.lib.kp_dp_relevance(self.handle, p.shape[0], _ptr(p), _ptr(f), _ptr(e), float(epsilon), float(lambd),
+                                             1 if sufficient else 0, _ptr(out), self._stream()), "kp_dp_relevance")
+        return out
 
     def contract(self, queries, mode=0):
         """Diagnostic: fused score -> softmax (0) / sigmoid (1) -> contract pass; returns (m[G], l[G], O[G,D])."""

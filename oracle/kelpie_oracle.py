@@ -720,3 +720,32 @@ def train_conve_full(state, training_triples, num_entities, num_relations, hp, n
     out = {k: v.detach().numpy() for k, v in P.items()}
     out.update({k: v.numpy() for k, v in S.items()})
     return out
+
+
+def dp_relevance(ent, rel, pred, fact, entity, epsilon, sufficient=False, lambd=1.0):
+    """Data-poisoning relevance for ComplEx (data_poisoning_engine.py:21-50 get_gradient via autograd, :53-94 necessary,
+    :97-131 sufficient), restated with torch autograd on the CPU in fp32 like the reference."""
+    E = torch.as_tensor(ent, dtype=torch.float32)
+    R = torch.as_tensor(rel, dtype=torch.float32)
+    d = E.shape[1] // 2
+
+    def score(lhs, r, rhs):  # complex.py:47-56
+        lhs, r, rhs = (lhs[:, :d], lhs[:, d:]), (r[:, :d], r[:, d:]), (rhs[:, :d], rhs[:, d:])
+        return torch.sum((lhs[0] * r[0] - lhs[1] * r[1]) * rhs[0] + (lhs[0] * r[1] + lhs[1] * r[0]) * rhs[1], 1, keepdim=True)
+
+    ps, pp, po = pred
+    lhs, r, rhs = E[ps].clone().view(1, -1), R[pp].view(1, -1), E[po].clone().view(1, -1)
+    x = lhs if entity == ps else rhs
+    x.requires_grad = True
+    score(lhs, r, rhs).backward()
+    g = x.grad[0]
+    pert = E[entity] + epsilon * g if sufficient else E[entity] - epsilon * g  # ComplEx maximises
+    s, p, o = fact
+    L, Rr, O = E[[s, s]].clone(), R[[p, p]], E[[o, o]].clone()
+    if s == entity:
+        L[1] = pert
+    else:
+        O[1] = pert
+    sc = score(L, Rr, O).detach().numpy()
+    a, b = sc[0], sc[1]
+    return float((-a + lambd * b)[0]) if sufficient else float((a - lambd * b)[0])

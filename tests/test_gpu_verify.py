@@ -88,3 +88,35 @@ def test_verify_sufficient_matches_reference():
     assert len(new_model.dataset.training_triples) == int(z["suf_n_train"])
     flat = [cv for e in evals for cv in e["conversions"]]
     _compare(flat, z["suf_scores"], z["suf_ranks"], new_model, [tuple(t) for t in c["to_convert"]])
+
+
+@pytest.mark.parametrize("kind", ["ComplEx", "ConvE"])
+def test_verify_necessary_flow_other_models(kind):
+    """The same flow for the other two model kinds (their device trainers: tests/test_fit_complex.py, test_fit_conve.py):
+    the ranks / scores BEFORE the retrain are those of predict_triples, removing the rule and retraining changes the
+    model, and the caller's dataset and model stay untouched."""
+    from kelpie_b200 import verify_explanations as ve
+    from kelpie_b200.data import Dataset
+    from kelpie_b200.link_prediction import MODEL_REGISTRY
+    from tests.golden_util import load, seed_all
+    g, meta, kg, w, _ = load(kind)
+    ds = Dataset("golden", g["train"], g["valid"], g["test"], kg.num_entities, kg.num_relations)
+    cls = MODEL_REGISTRY[kind]["class"]
+    seed_all(3)
+    model = cls(ds, cls.get_hyperparams_class()(**meta["params"]), init_random=True)
+    model.eval()
+    training = (dict(optimizer_name="Adagrad", batch_size=128, epochs=2, lr=0.043, decay1=0.9, decay2=0.999, regularizer_name="N3",
+                     regularizer_weight=0) if kind == "ComplEx"
+                else dict(batch_size=128, label_smoothing=0.1, lr=0.003, decay=0.995, epochs=2))
+    preds = [tuple(int(x) for x in t) for t in g["test"][:4]]
+    rules = {p: [tuple(int(x) for x in t) for t in ds.entity_to_training_triples[p[0]][:2]] for p in preds}
+    before = model.predict_triples(np.array(preds))
+    ent0 = model.entity_embeddings.detach().clone()
+    evals, new_model = ve.verify_necessary(model, ds, rules, {"model_params": meta["params"], "training": training})
+    for ev, b, p in zip(evals, before, preds):
+        assert ev["triple_to_explain"] == p and ev["rank"] == str(b["rank"]["tail"]) and ev["score"] == str(b["score"]["tail"])
+        assert float(ev["new_score"]) == float(ev["new_score"])  # finite
+    removed = sum(len(set(r)) for r in rules.values())
+    assert len(ds.training_triples) == len(g["train"]) and len(new_model.dataset.training_triples) <= len(g["train"]) - 1
+    assert torch.equal(ent0, model.entity_embeddings.detach()) and new_model is not model
+    assert removed >= 1 and any(ev["new_rank"] != ev["rank"] or ev["new_score"] != ev["score"] for ev in evals)
