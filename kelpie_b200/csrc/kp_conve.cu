@@ -8,7 +8,6 @@
 
 namespace {
 
-constexpr int CV_THREADS = 256;
 
 struct ConvK {
   int Q, N, R2, D, H, F, hidden, stride;
@@ -36,39 +35,74 @@ __device__ __forceinline__ void bn_affine(const float* bn, int n, int i, float& 
 }
 
 // Stage 1 (one CTA per pair): stacked image -> BN1 (+input dropout) -> Conv 3x3 -> BN2 -> ReLU
-// (+Dropout2d) -> feat[q, hidden]
-__global__ void __launch_bounds__(CV_THREADS) conve_conv_kernel(const ConvK p) {
+// (+Dropout2d) -> feat[q, hidden].
+// A warp owns a group of 4 filters (their 36 weights and BN2 affines sit in registers) and its lanes sweep the 38 x W2
+// output positions: every image tap read from shared memory feeds 4 FMAs and every store instruction of the warp
+// writes 32 consecutive floats of one filter's plane.
+constexpr int CV_CONV_THREADS = 256;
+__global__ void __launch_bounds__(CV_CONV_THREADS) conve_conv_kernel(const ConvK p) {
   extern __shared__ float sm[];
-  const int H = p.H, W2 = H - 2, D = p.D;
+  const int H = p.H, W2 = H - 2, D = p.D, F = p.F;
   const int img_sz = 40 * H;
-  float* img = sm;  // [40*H]
-  const int tid = threadIdx.x, q = blockIdx.x;
+  float* img = sm;            // [40*H]
+  float* wsm = img + img_sz;  // [9F] weights | [F] bias | [F] alpha2 | [F] beta2
+  float* bsm = wsm + 9 * F;
+  float* a2s = bsm + F;
+  float* b2s = a2s + F;
+  const int tid = threadIdx.x, q = blockIdx.x, lane = tid & 31, warp = tid >> 5;
   float a1, b1;
   bn_affine(p.bn1, 1, 0, a1, b1);
   const int s = p.lhs_ids ? p.lhs_ids[(size_t)q * p.stride] : p.N, r = p.rel_ids[(size_t)q * p.stride];
   const float* l = (s == p.N) ? p.mimic + (size_t)(p.mimic_index ? p.mimic_index[q] : q) * D : p.ent + (size_t)s * D;
-  for (int k = tid; k < img_sz; k += CV_THREADS) {
+  const bool drop = p.drop_ids != nullptr;
+  const int pid = drop ? p.drop_ids[q] : 0;
+  for (int k = tid; k < img_sz; k += CV_CONV_THREADS) {
     float v = (k < D) ? l[k] : p.rel[(size_t)r * D + (k - D)];
     v = v * a1 + b1;
-    if (p.drop_ids && p.p_in > 0.f) v *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_INPUT + k, p.p_in);
+    if (drop && p.p_in > 0.f) v *= kp_drop_scale(p.seed, pid, p.step, KP_DROP_INPUT + k, p.p_in);
     img[k] = v;
+  }
+  for (int k = tid; k < 9 * F; k += CV_CONV_THREADS) wsm[k] = p.conv_w[k];
+  for (int c = tid; c < F; c += CV_CONV_THREADS) {
+    float a2, b2;
+    bn_affine(p.bn2, F, c, a2, b2);
+    if (drop && p.p_fm > 0.f) {  // Dropout2d scales a whole channel; relu(a x + b) * s = relu(s a x + s b) for s >= 0
+      const float sc = kp_drop_scale(p.seed, pid, p.step, KP_DROP_FEATURE + c, p.p_fm);
+      a2 *= sc;
+      b2 *= sc;
+    }
+    bsm[c] = p.conv_b[c];
+    a2s[c] = a2;
+    b2s[c] = b2;
   }
   __syncthreads();
   const int per_f = 38 * W2;
-  for (int o = tid; o < p.hidden; o += CV_THREADS) {
-    const int c = o / per_f, y = (o % per_f) / W2, x = o % W2;
-    const float* im = img + y * H + x;
-    const float* w = p.conv_w + c * 9;
-    float acc = p.conv_b[c];
+  for (int c0 = warp * 4; c0 < F; c0 += (CV_CONV_THREADS / 32) * 4) {
+    float w[4][9], bias[4], a2[4], b2[4];
 #pragma unroll
-    for (int dy = 0; dy < 3; ++dy)
+    for (int f = 0; f < 4; ++f) {
 #pragma unroll
-      for (int dx = 0; dx < 3; ++dx) acc = __fmaf_rn(w[dy * 3 + dx], im[dy * H + dx], acc);
-    float a2, b2;
-    bn_affine(p.bn2, p.F, c, a2, b2);
-    acc = fmaxf(acc * a2 + b2, 0.f);
-    if (p.drop_ids && p.p_fm > 0.f) acc *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_FEATURE + c, p.p_fm);
-    p.feat_out[(size_t)q * p.hidden + o] = acc;
+      for (int k = 0; k < 9; ++k) w[f][k] = wsm[(c0 + f) * 9 + k];
+      bias[f] = bsm[c0 + f];
+      a2[f] = a2s[c0 + f];
+      b2[f] = b2s[c0 + f];
+    }
+    float* out = p.feat_out + (size_t)q * p.hidden + (size_t)c0 * per_f;
+    for (int pos = lane; pos < per_f; pos += 32) {
+      const int y = pos / W2;
+      const float* tap = img + pos + 2 * y;  // y * H + x with H = W2 + 2
+      float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float v = tap[dy * H + dx];
+#pragma unroll
+          for (int f = 0; f < 4; ++f) acc[f] = __fmaf_rn(w[f][dy * 3 + dx], v, acc[f]);
+        }
+#pragma unroll
+      for (int f = 0; f < 4; ++f) out[(size_t)f * per_f + pos] = fmaxf(__fmaf_rn(acc[f], a2[f], b2[f]), 0.f);
+    }
   }
 }
 
@@ -116,6 +150,7 @@ int upload(kp_ctx* ctx, const T* src, size_t n, T** dst) {
 
 int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
   const int D = ctx->D, H = D / 20;
+  if (w->n_filters % 4 != 0) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE filter count %d must be a multiple of 4 (the reference fixes 32)", w->n_filters);
   if (w->n_filters <= 0 || w->hidden != w->n_filters * 38 * (H - 2))
     KP_FAIL(ctx, KP_EINVAL, "ConvE hidden size %d != %d * 38 * %d", w->hidden, w->n_filters, H - 2);
   if (w->hidden % 4 != 0) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size must be a multiple of 4");
@@ -211,7 +246,7 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
     c.feat_out = feat_out ? feat_out + (size_t)q0 * p.hidden : scratch;
     {
       KpTimer timer(ctx, kp_ctx::T_CONV, st);
-      conve_conv_kernel<<<n, CV_THREADS, (size_t)40 * p.H * sizeof(float), st>>>(c);
+      conve_conv_kernel<<<n, CV_CONV_THREADS, ((size_t)40 * p.H + 12 * p.F) * sizeof(float), st>>>(c);
     }
     KP_LAUNCHED(ctx, 1);
     int rc = kp_conve_fc(ctx, true, n, c.feat_out, c.x_out, feat_out ? 0 : (size_t)chunk * p.hidden * sizeof(float) + 1024, st);

@@ -665,27 +665,27 @@ extern "C" int kp_conve_fit_steps(kp_vfit* f, int64_t n_steps, const int64_t* st
       if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
       vfit_bn2_relu<<<(int)blocks, 256, 0, st>>>(d, f->p, ord, f->C, f->feat, S1, S2);
     }
-    rc = (f->fp32_mask & 1) ? kp_sgemm(ctx, true, B, D, hidden, f->feat, hidden, f->p.fc_w, hidden, f->H, D, st)
+    rc = (f->fp32_mask & 1) ? kp_sgemm(ctx, true, B, D, hidden, f->feat, hidden, f->p.fc_w, hidden, f->H, D, st, -1, true)
                             : kp_gemm_umma_dyn(ctx, f->feat, hidden, false, B, f->p.fc_w, hidden, false, D, hidden, f->H, D, 0, st);
     if (rc != KP_OK) goto gemm_failed;
     vfit_bn3_fwd<<<colgrid, colblock, 0, st>>>(d, f->p, ord, f->H, f->X, f->st3);
-    rc = (f->fp32_mask & 2) ? kp_sgemm(ctx, true, B, N, D, f->X, D, f->p.ent, D, f->Z, (int)f->ldz, st)
+    rc = (f->fp32_mask & 2) ? kp_sgemm(ctx, true, B, N, D, f->X, D, f->p.ent, D, f->Z, (int)f->ldz, st, -1, true)
                             : kp_gemm_umma_dyn(ctx, f->X, D, false, B, f->p.ent, D, false, N, D, f->Z, f->ldz, 0, st);
     if (rc != KP_OK) goto gemm_failed;
     vfit_bce<<<B, 256, 0, st>>>(B, N, f->ldz, f->Z, ord, f->pos_off, f->pos_ids, w, base, loss_out ? loss_out + k : nullptr);
-    rc = (f->fp32_mask & 4) ? kp_sgemm(ctx, false, B, D, (int)f->ldz, f->Z, (int)f->ldz, f->p.ent, D, f->dX, D, st, N)
+    rc = (f->fp32_mask & 4) ? kp_sgemm(ctx, false, B, D, (int)f->ldz, f->Z, (int)f->ldz, f->p.ent, D, f->dX, D, st, N, true)
                             : kp_gemm_umma_dyn(ctx, f->Z, f->ldz, false, B, f->p.ent, D, true, D, N, f->dX, D, 0, st);
     if (rc != KP_OK || (rc = kp_gemm_umma_dyn(ctx, f->Z, f->ldz, true, N, f->X, D, true, D, B, gE, D, 0, st)) != KP_OK) goto gemm_failed;
     vfit_bn3_bwd<<<colgrid, colblock, 0, st>>>(d, f->p, ord, f->H, f->X, f->dX, f->st3, f->dH, g + sg[SEG_BN3_W].off, g + sg[SEG_BN3_B].off, gFB);
     if (f->fp32_mask & 16) {
       const int Bpad = (B + 3) / 4 * 4;
       vfit_transpose<<<dim3((D + 31) / 32, (Bpad + 31) / 32), dim3(32, 8), 0, st>>>(B, Bpad, D, f->dH, f->dHt);
-      rc = kp_sgemm(ctx, false, D, hidden, Bpad, f->dHt, Bpad, f->feat, hidden, gW, hidden, st, B);
+      rc = kp_sgemm(ctx, false, D, hidden, Bpad, f->dHt, Bpad, f->feat, hidden, gW, hidden, st, B, true);
     } else {
       rc = kp_gemm_umma_dyn(ctx, f->dH, D, true, D, f->feat, hidden, true, hidden, B, gW, hidden, 0, st);
     }
     if (rc != KP_OK) goto gemm_failed;
-    rc = (f->fp32_mask & 32) ? kp_sgemm(ctx, false, B, hidden, D, f->dH, D, f->p.fc_w, hidden, f->dfeat, hidden, st)
+    rc = (f->fp32_mask & 32) ? kp_sgemm(ctx, false, B, hidden, D, f->dH, D, f->p.fc_w, hidden, f->dfeat, hidden, st, -1, true)
                              : kp_gemm_umma_dyn(ctx, f->dH, D, false, B, f->p.fc_w, hidden, true, hidden, D, f->dfeat, hidden, 0, st);
     if (rc != KP_OK) goto gemm_failed;
     vfit_bn2_bwd<<<B, 256, 0, st>>>(d, f->p, ord, f->C, f->feat, f->dfeat, S2, B2);

@@ -104,7 +104,79 @@ struct CvBack {
 
 // One CTA per pair: ReLU / BN2 (/Dropout2d) backward, Conv^T restricted to the lhs half of the
 // 40 x H image, BN1 (/input dropout) backward.
+// Phase 1 stages d conv (hidden floats) in shared memory with an ODD per-filter stride, so that phase 2 can put one
+// filter on every lane without bank conflicts.  Phase 2: a warp owns one row y of the lhs image; lane c accumulates
+// filter c's contribution to the H pixels of that row from the (up to) three conv-output rows y, y-1, y-2 held in
+// registers, then the H sums are reduced over the lanes.
+template <int H>
 __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
+  extern __shared__ float bsm[];
+  constexpr int W2 = H - 2, per_f = 38 * W2, stride = per_f | 1;
+  const int D = p.D, hidden = p.hidden, F = p.F;
+  float* dcv = bsm;              // [F][stride]
+  float* wsm = dcv + F * stride;  // [9F]
+  float* a2s = wsm + 9 * F;       // [F] BN2 scale (x Dropout2d scale)
+  const int tid = threadIdx.x, g = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int c = tid; c < F; c += CT) {
+    float a2 = p.bn2[c] / sqrtf(p.bn2[3 * F + c] + 1e-5f);
+    if (p.p_fm > 0.f) a2 *= kp_drop_scale(p.seed, p.pair[g], p.step, KP_DROP_FEATURE + c, p.p_fm);
+    a2s[c] = a2;
+  }
+  for (int k = tid; k < 9 * F; k += CT) wsm[k] = p.conv_w[k];
+  __syncthreads();
+  const float4* feat4 = reinterpret_cast<const float4*>(p.feat + (size_t)g * hidden);
+  const float4* dfeat4 = reinterpret_cast<const float4*>(p.dfeat + (size_t)g * hidden);
+  for (int i4 = tid; i4 < hidden / 4; i4 += CT) {  // per_f = 38 * W2 is even, hidden a multiple of 4: a float4 may straddle two filters
+    const float4 f = feat4[i4], d = dfeat4[i4];
+    const float fv[4] = {f.x, f.y, f.z, f.w}, dv[4] = {d.x, d.y, d.z, d.w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i4 * 4 + j, c = i / per_f;
+      dcv[c * stride + (i - c * per_f)] = fv[j] > 0.f ? dv[j] * a2s[c] : 0.f;  // dropped channels have feat == 0
+    }
+  }
+  __syncthreads();
+  const float a1 = p.bn1[0] / sqrtf(p.bn1[3] + 1e-5f);
+  for (int y = warp; y < 20; y += CT / 32) {
+    float acc[H];
+#pragma unroll
+    for (int x = 0; x < H; ++x) acc[x] = 0.f;
+    for (int c = lane; c < F; c += 32) {
+      const float* w = wsm + 9 * c;
+#pragma unroll
+      for (int dy = 0; dy < 3; ++dy) {
+        const int yy = y - dy;  // conv-output row; yy <= 19 < 38 always
+        if (yy < 0) continue;
+        const float* src = dcv + c * stride + yy * W2;
+        float r[W2];
+#pragma unroll
+        for (int xx = 0; xx < W2; ++xx) r[xx] = src[xx];
+#pragma unroll
+        for (int dx = 0; dx < 3; ++dx) {
+          const float wv = w[dy * 3 + dx];
+#pragma unroll
+          for (int xx = 0; xx < W2; ++xx) acc[xx + dx] = __fmaf_rn(wv, r[xx], acc[xx + dx]);
+        }
+      }
+    }
+#pragma unroll
+    for (int x = 0; x < H; ++x) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) acc[x] += __shfl_xor_sync(0xffffffffu, acc[x], o);
+    }
+    if (lane < H) {
+      float v = acc[0];
+#pragma unroll
+      for (int x = 1; x < H; ++x) v = lane == x ? acc[x] : v;
+      const int k = y * H + lane;
+      if (p.p_in > 0.f) v *= kp_drop_scale(p.seed, p.pair[g], p.step, KP_DROP_INPUT + k, p.p_in);
+      p.glhs[(size_t)g * D + k] = v * a1;
+    }
+  }
+}
+
+// any other image width: one thread per lhs pixel
+__global__ void __launch_bounds__(CT) cv_backward_generic(const CvBack p) {
   extern __shared__ float bsm[];
   const int D = p.D, H = p.H, W2 = H - 2, hidden = p.hidden, per_f = 38 * W2;
   float* dcv = bsm;  // [hidden]
@@ -248,10 +320,13 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   const int cb = (C + 127) / 128;
   int64_t GA = 0, GB = 0;
   static bool configured = false;
-  const size_t back_smem = (size_t)hidden * sizeof(float);
+  const int Hc = ctx->cv.H, Fc = ctx->cv.n_filters;
+  const size_t back_smem = ((size_t)Fc * ((38 * (Hc - 2)) | 1) + 10 * Fc) * sizeof(float);
   if (back_smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", hidden);
   if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     configured = true;
   }
   const bool static_plan = spe_max <= 1;
@@ -295,7 +370,12 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
       k.pair = pl.a_truth; k.seed = seed; k.step = (int)t; k.p_in = ctx->cv.drop_in; k.p_fm = ctx->cv.drop_fm;
       KP_LAUNCHED(ctx, 1);
       if ((rc = kp_conve_fc(ctx, false, (int)GA, dh, dfeat, 0, st)) != KP_OK) return rc;
-      cv_backward<<<(int)GA, CT, back_smem, st>>>(k);
+      {
+        KpTimer timer(ctx, kp_ctx::T_CONV, st);
+        if (Hc == 10) cv_backward<10><<<(int)GA, CT, back_smem, st>>>(k);
+        else if (Hc == 4) cv_backward<4><<<(int)GA, CT, back_smem, st>>>(k);
+        else cv_backward_generic<<<(int)GA, CT, back_smem, st>>>(k);
+      }
       KP_LAUNCHED(ctx, 1);
     }
     if (GA + GB > 0) {

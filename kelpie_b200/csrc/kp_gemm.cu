@@ -97,14 +97,15 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
 }  // namespace
 
 int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-             int ldc, cudaStream_t st, int k_rows_b) {
+             int ldc, cudaStream_t st, int k_rows_b, bool split_k) {
   if (M <= 0 || N <= 0) return KP_OK;
   if (K % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "sgemm needs K and leading dimensions multiple of 4");
   dim3 grid((M + GM - 1) / GM, (N + GN - 1) / GN);
-  // few output tiles and a long K: cut K over blockIdx.z (partial sums reduced with fp32 atomics into a zeroed C)
+  // opt-in (the sum order becomes unordered): few output tiles and a long K -> cut K over blockIdx.z, partial sums
+  // reduced with fp32 atomics into a zeroed C
   int k_per_split = 0;
   const long long tiles = (long long)grid.x * grid.y;
-  if (tiles * 2 <= ctx->sm_count && K >= 64 * GK) {
+  if (split_k && tiles * 2 <= ctx->sm_count && K >= 64 * GK) {
     int splits = (int)((2LL * ctx->sm_count + tiles - 1) / tiles);
     if (splits > K / (8 * GK)) splits = K / (8 * GK);
     if (splits > 1) {

@@ -194,9 +194,10 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
                          const float* mimic, const int32_t* mimic_index, float* x_out, float* feat_out,
                          cudaStream_t st, const int32_t* drop_ids = nullptr, unsigned long long seed = 0,
                          int step = 0);
-// k_rows_b (non-transposed B only): rows of B that exist when K was rounded up over a zero-padded A (-1: K)
+// k_rows_b (non-transposed B only): rows of B that exist when K was rounded up over a zero-padded A (-1: K);
+// split_k: allow cutting a long K over blockIdx.z (atomic reduction: unordered sums, only for the trainers)
 int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
-             int ldc, cudaStream_t st, int k_rows_b = -1);
+             int ldc, cudaStream_t st, int k_rows_b = -1, bool split_k = false);
 int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
                           int groups_per_chunk, int n_chunks, int n_qt, int n_strips, int tps, int mode, float* part_m,
                           float* part_l, float* part_O, cudaStream_t st);
