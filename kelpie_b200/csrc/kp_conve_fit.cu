@@ -8,7 +8,7 @@
 //   vfit_gather      X0[i] = [E[lhs_i] ; R[rel_i]], batch sums for batch-norm 1                   CTA per pair
 //   vfit_conv_fwd    in = dropout(bn1(X0));  C = conv3x3(in) + b;  per-filter sums for bn2          CTA per pair
 //   vfit_bn2_relu    feat = dropout2d(relu(bn2(C)));  running statistics of bn1 / bn2               elementwise
-//   GEMM             H[B, D] = feat W^T                                tcgen05, bf16x3 split   (kp_gemm_umma.cu)
+//   GEMM             H[B, D] = feat W^T                                tcgen05, tf32x3 split   (kp_gemm_umma.cu)
 //   vfit_bn3_fwd     H = dropout(H + b);  X = relu(bn3(H));  running statistics of bn3              CTA per 32 columns
 //   GEMM             Z[B, N] = X E^T
 //   vfit_bce         P = (sigmoid(Z) - target) / (B N) in place, loss                               CTA per pair
@@ -52,12 +52,14 @@ struct kp_vfit {
         *dfeat = nullptr, *dX0 = nullptr, *st3 = nullptr;
   double* stats = nullptr;  // S1[2] | S2[2F] | B2[2F] | B1[2]
   float* dHt = nullptr;     // [D, ceil4(max_batch)] transpose of dH for the fp32 weight-gradient GEMM
-  // bit g set: GEMM g (0 H, 1 Z, 2 dX, 4 gW, 5 dfeat) runs as an exact fp32 CUDA-core GEMM instead of the bf16x3 tcgen05 GEMM.
-  // Default: all five.  Measured (tools/debug_conve_fit.py): relu gating + Adam's scale invariance turn the
-  // 1e-5 perturbations of bf16x3 into 1e-3 L-inf deviations of the trained tensors within 72 steps, fp32 stays at the
-  // reference's own fp32-vs-fp64 noise floor (1e-5).  gE = P^T X (no cancellation) always runs on the tensor cores.
-  // KP_VFIT_FP32=<mask> overrides (diagnostics).
-  int fp32_mask = 55;
+  // Precision of the six GEMMs (bit g: 0 H, 1 Z, 2 dX, 3 gE, 4 gW, 5 dfeat).  Measured (tools/debug_conve_fit.py):
+  // relu gating + Adam's scale invariance turn the 1e-5 perturbations of bf16x3 products into 1e-3 L-inf deviations of
+  // the trained tensors within 72 steps, while tf32x3 (error ~2^-21 per product, kind::tf32 at half the bf16 MMA rate)
+  // stays at the reference's own fp32-vs-fp64 noise floor (1e-5), like exact fp32.  Default: the five GEMMs on the
+  // activation path as tf32x3 on the tensor cores; gE = P^T X (no cancellation, the largest GEMM) as bf16x3.
+  // KP_VFIT_TF32=<mask> / KP_VFIT_FP32=<mask> override (diagnostics): tf32x3 wins over fp32 CUDA cores wins over bf16x3.
+  int tf32_mask = 55;
+  int fp32_mask = 0;
   long long t = 0;
   int64_t launches = 0;
   std::string err;
@@ -224,17 +226,17 @@ __global__ void __launch_bounds__(256) vfit_bn2_relu(VDims d, kp_conve_params p,
   }
 }
 
-// CTA = 32 columns x 8 row groups.  H <- dropout(H + b) (the batch-norm input, kept for the backward); X = relu(bn3(H))
-__global__ void __launch_bounds__(256) vfit_bn3_fwd(VDims d, kp_conve_params p, const int32_t* __restrict__ order, float* __restrict__ H,
+// CTA = 32 columns x 32 row groups.  H <- dropout(H + b) (the batch-norm input, kept for the backward); X = relu(bn3(H))
+__global__ void __launch_bounds__(1024) vfit_bn3_fwd(VDims d, kp_conve_params p, const int32_t* __restrict__ order, float* __restrict__ H,
                                                     float* __restrict__ X, float* __restrict__ st3) {
-  __shared__ double red[2][8][32];
+  __shared__ double red[2][32][32];
   __shared__ float bc[2][32];
   const int cx = threadIdx.x, ry = threadIdx.y, c = blockIdx.x * 32 + cx;
   const bool live = c < d.D;
   double s = 0.0, ss = 0.0;
   if (live) {
     const float bias = p.fc_b[c];
-    for (int i = ry; i < d.B; i += 8) {
+    for (int i = ry; i < d.B; i += 32) {
       float h = H[(size_t)i * d.D + c] + bias;
       if (d.p_hid > 0.f) h *= drop(d, d.p_hid, order[i], KP_DROP_HIDDEN + c);
       H[(size_t)i * d.D + c] = h;
@@ -246,7 +248,7 @@ __global__ void __launch_bounds__(256) vfit_bn3_fwd(VDims d, kp_conve_params p, 
   red[1][ry][cx] = ss;
   __syncthreads();
   if (ry == 0 && live) {
-    for (int k = 1; k < 8; ++k) s += red[0][k][cx], ss += red[1][k][cx];
+    for (int k = 1; k < 32; ++k) s += red[0][k][cx], ss += red[1][k][cx];
     float mean, var;
     if (d.train_bn) {
       bn_moments(s, ss, (double)d.B, mean, var);
@@ -265,7 +267,7 @@ __global__ void __launch_bounds__(256) vfit_bn3_fwd(VDims d, kp_conve_params p, 
   __syncthreads();
   if (live) {
     const float sc = bc[0][cx], sh = bc[1][cx];
-    for (int i = ry; i < d.B; i += 8) X[(size_t)i * d.D + c] = fmaxf(fmaf(H[(size_t)i * d.D + c], sc, sh), 0.f);
+    for (int i = ry; i < d.B; i += 32) X[(size_t)i * d.D + c] = fmaxf(fmaf(H[(size_t)i * d.D + c], sc, sh), 0.f);
   }
 }
 
@@ -279,15 +281,17 @@ __global__ void __launch_bounds__(256) vfit_bce(int B, int N, long long ldz, flo
   float* z = Z + (size_t)i * ldz;
   const int64_t e0 = pos_off[pid], e1 = pos_off[pid + 1];
   const float inv = 1.f / ((float)B * (float)N);
-  double ls = 0.0, unused = 0.0;
-  for (int64_t e = e0 + tid; e < e1; e += 256) ls -= (double)(w * z[pos_ids[e]]);
+  float lsf = 0.f;  // per-thread partial in fp32 (<= ldz / 256 terms), reduced in fp64
+  if (loss)
+    for (int64_t e = e0 + tid; e < e1; e += 256) lsf -= w * z[pos_ids[e]];
   __syncthreads();
   for (int j = tid; j < (int)ldz; j += 256) {
     if (j < N) {
       const float x = z[j];
-      const float sp = fmaxf(x, 0.f) + log1pf(expf(-fabsf(x)));
-      ls += (double)(sp - base * x);
-      z[j] = (1.f / (1.f + expf(-x)) - base) * inv;
+      const float en = expf(-fabsf(x));             // exp(-|x|) in (0, 1]
+      const float sig_abs = 1.f / (1.f + en);       // sigmoid(|x|)
+      if (loss) lsf += fmaxf(x, 0.f) + log1pf(en) - base * x;
+      z[j] = ((x >= 0.f ? sig_abs : en * sig_abs) - base) * inv;
     } else {
       z[j] = 0.f;
     }
@@ -295,24 +299,25 @@ __global__ void __launch_bounds__(256) vfit_bce(int B, int N, long long ldz, flo
   __syncthreads();
   for (int64_t e = e0 + tid; e < e1; e += 256) z[pos_ids[e]] -= w * inv;
   if (loss) {
+    double ls = (double)lsf, unused = 0.0;
     block_sum2(ls, unused, red);
     if (tid == 0) atomicAdd(loss, (float)(ls * (double)inv));
   }
 }
 
-// backward through relu / bn3 / hidden dropout; CTA = 32 columns x 8 row groups
-__global__ void __launch_bounds__(256) vfit_bn3_bwd(VDims d, kp_conve_params p, const int32_t* __restrict__ order, const float* __restrict__ H,
+// backward through relu / bn3 / hidden dropout; CTA = 32 columns x 32 row groups
+__global__ void __launch_bounds__(1024) vfit_bn3_bwd(VDims d, kp_conve_params p, const int32_t* __restrict__ order, const float* __restrict__ H,
                                                     const float* __restrict__ X, const float* __restrict__ dX, const float* __restrict__ st3,
                                                     float* __restrict__ dH, float* __restrict__ g_w, float* __restrict__ g_b,
                                                     float* __restrict__ g_fcb) {
-  __shared__ double red[2][8][32];
+  __shared__ double red[2][32][32];
   __shared__ float bc[2][32];
   const int cx = threadIdx.x, ry = threadIdx.y, c = blockIdx.x * 32 + cx;
   const bool live = c < d.D;
   const float mean = live ? st3[c] : 0.f, istd = live ? st3[d.D + c] : 0.f;
   double a = 0.0, b = 0.0;
   if (live)
-    for (int i = ry; i < d.B; i += 8) {
+    for (int i = ry; i < d.B; i += 32) {
       const size_t o = (size_t)i * d.D + c;
       const float dy = X[o] > 0.f ? dX[o] : 0.f;
       a += dy;
@@ -322,7 +327,7 @@ __global__ void __launch_bounds__(256) vfit_bn3_bwd(VDims d, kp_conve_params p, 
   red[1][ry][cx] = b;
   __syncthreads();
   if (ry == 0 && live) {
-    for (int k = 1; k < 8; ++k) a += red[0][k][cx], b += red[1][k][cx];
+    for (int k = 1; k < 32; ++k) a += red[0][k][cx], b += red[1][k][cx];
     g_b[c] = (float)a;
     g_w[c] = (float)b;
     bc[0][cx] = (float)(a / d.B);
@@ -332,7 +337,7 @@ __global__ void __launch_bounds__(256) vfit_bn3_bwd(VDims d, kp_conve_params p, 
   double sb = 0.0;
   if (live) {
     const float am = d.train_bn ? bc[0][cx] : 0.f, bm = d.train_bn ? bc[1][cx] : 0.f, gs = p.bn3_w[c] * istd;
-    for (int i = ry; i < d.B; i += 8) {
+    for (int i = ry; i < d.B; i += 32) {
       const size_t o = (size_t)i * d.D + c;
       const float dy = X[o] > 0.f ? dX[o] : 0.f;
       float dh = gs * (dy - am - (H[o] - mean) * istd * bm);
@@ -345,7 +350,7 @@ __global__ void __launch_bounds__(256) vfit_bn3_bwd(VDims d, kp_conve_params p, 
   red[0][ry][cx] = sb;
   __syncthreads();
   if (ry == 0 && live) {
-    for (int k = 1; k < 8; ++k) sb += red[0][k][cx];
+    for (int k = 1; k < 32; ++k) sb += red[0][k][cx];
     g_fcb[c] = (float)sb;
   }
 }
@@ -584,6 +589,7 @@ extern "C" int kp_conve_fit_create(int device, int64_t n_entities, int64_t n_rel
   f->pos_off = pos_off;
   f->pos_ids = pos_ids;
   if (const char* e = getenv("KP_VFIT_FP32")) f->fp32_mask = atoi(e);
+  if (const char* e = getenv("KP_VFIT_TF32")) f->tf32_mask = atoi(e);
   const long long cnt[NSEG] = {(long long)n_entities * dim, (long long)n_relations2 * dim, 9ll * f->F, f->F, (long long)dim * f->hidden, dim, 1, 1,
                                f->F, f->F, dim, dim};
   float* par[NSEG] = {params->ent, params->rel, params->conv_w, params->conv_b, params->fc_w, params->fc_b, params->bn1_w, params->bn1_b,
@@ -646,7 +652,7 @@ extern "C" int kp_conve_fit_steps(kp_vfit* f, int64_t n_steps, const int64_t* st
   for (int s = 0; s < NSEG; ++s) max_n = sg[s].n > max_n ? sg[s].n : max_n;
   int adam_blocks = (int)((max_n + 255) / 256);
   if (adam_blocks > ctx->sm_count * 8) adam_blocks = ctx->sm_count * 8;
-  const dim3 colgrid((D + 31) / 32), colblock(32, 8);
+  const dim3 colgrid((D + 31) / 32), colblock(32, 32);
   for (int64_t k = 0; k < n_steps; ++k) {
     const int B = (int)(step_off[k + 1] - step_off[k]);
     if (B <= 0) continue;
@@ -665,28 +671,30 @@ extern "C" int kp_conve_fit_steps(kp_vfit* f, int64_t n_steps, const int64_t* st
       if (blocks > ctx->sm_count * 8) blocks = ctx->sm_count * 8;
       vfit_bn2_relu<<<(int)blocks, 256, 0, st>>>(d, f->p, ord, f->C, f->feat, S1, S2);
     }
-    rc = (f->fp32_mask & 1) ? kp_sgemm(ctx, true, B, D, hidden, f->feat, hidden, f->p.fc_w, hidden, f->H, D, st, -1, true)
-                            : kp_gemm_umma_dyn(ctx, f->feat, hidden, false, B, f->p.fc_w, hidden, false, D, hidden, f->H, D, 0, st);
+    rc = (f->fp32_mask & ~f->tf32_mask & 1) ? kp_sgemm(ctx, true, B, D, hidden, f->feat, hidden, f->p.fc_w, hidden, f->H, D, st, -1, true)
+                                            : kp_gemm_umma_dyn(ctx, f->feat, hidden, false, B, f->p.fc_w, hidden, false, D, hidden, f->H, D, 0, st,
+                                                               f->tf32_mask & 1);
     if (rc != KP_OK) goto gemm_failed;
     vfit_bn3_fwd<<<colgrid, colblock, 0, st>>>(d, f->p, ord, f->H, f->X, f->st3);
-    rc = (f->fp32_mask & 2) ? kp_sgemm(ctx, true, B, N, D, f->X, D, f->p.ent, D, f->Z, (int)f->ldz, st, -1, true)
-                            : kp_gemm_umma_dyn(ctx, f->X, D, false, B, f->p.ent, D, false, N, D, f->Z, f->ldz, 0, st);
+    rc = (f->fp32_mask & ~f->tf32_mask & 2) ? kp_sgemm(ctx, true, B, N, D, f->X, D, f->p.ent, D, f->Z, (int)f->ldz, st, -1, true)
+                                            : kp_gemm_umma_dyn(ctx, f->X, D, false, B, f->p.ent, D, false, N, D, f->Z, f->ldz, 0, st, f->tf32_mask & 2);
     if (rc != KP_OK) goto gemm_failed;
     vfit_bce<<<B, 256, 0, st>>>(B, N, f->ldz, f->Z, ord, f->pos_off, f->pos_ids, w, base, loss_out ? loss_out + k : nullptr);
-    rc = (f->fp32_mask & 4) ? kp_sgemm(ctx, false, B, D, (int)f->ldz, f->Z, (int)f->ldz, f->p.ent, D, f->dX, D, st, N, true)
-                            : kp_gemm_umma_dyn(ctx, f->Z, f->ldz, false, B, f->p.ent, D, true, D, N, f->dX, D, 0, st);
-    if (rc != KP_OK || (rc = kp_gemm_umma_dyn(ctx, f->Z, f->ldz, true, N, f->X, D, true, D, B, gE, D, 0, st)) != KP_OK) goto gemm_failed;
+    rc = (f->fp32_mask & ~f->tf32_mask & 4) ? kp_sgemm(ctx, false, B, D, (int)f->ldz, f->Z, (int)f->ldz, f->p.ent, D, f->dX, D, st, N, true)
+                                            : kp_gemm_umma_dyn(ctx, f->Z, f->ldz, false, B, f->p.ent, D, true, D, N, f->dX, D, 0, st, f->tf32_mask & 4);
+    if (rc != KP_OK || (rc = kp_gemm_umma_dyn(ctx, f->Z, f->ldz, true, N, f->X, D, true, D, B, gE, D, 0, st, f->tf32_mask & 8)) != KP_OK) goto gemm_failed;
     vfit_bn3_bwd<<<colgrid, colblock, 0, st>>>(d, f->p, ord, f->H, f->X, f->dX, f->st3, f->dH, g + sg[SEG_BN3_W].off, g + sg[SEG_BN3_B].off, gFB);
-    if (f->fp32_mask & 16) {
+    if (f->fp32_mask & ~f->tf32_mask & 16) {
       const int Bpad = (B + 3) / 4 * 4;
       vfit_transpose<<<dim3((D + 31) / 32, (Bpad + 31) / 32), dim3(32, 8), 0, st>>>(B, Bpad, D, f->dH, f->dHt);
       rc = kp_sgemm(ctx, false, D, hidden, Bpad, f->dHt, Bpad, f->feat, hidden, gW, hidden, st, B, true);
     } else {
-      rc = kp_gemm_umma_dyn(ctx, f->dH, D, true, D, f->feat, hidden, true, hidden, B, gW, hidden, 0, st);
+      rc = kp_gemm_umma_dyn(ctx, f->dH, D, true, D, f->feat, hidden, true, hidden, B, gW, hidden, 0, st, f->tf32_mask & 16);
     }
     if (rc != KP_OK) goto gemm_failed;
-    rc = (f->fp32_mask & 32) ? kp_sgemm(ctx, false, B, hidden, D, f->dH, D, f->p.fc_w, hidden, f->dfeat, hidden, st, -1, true)
-                             : kp_gemm_umma_dyn(ctx, f->dH, D, false, B, f->p.fc_w, hidden, true, hidden, D, f->dfeat, hidden, 0, st);
+    rc = (f->fp32_mask & ~f->tf32_mask & 32) ? kp_sgemm(ctx, false, B, hidden, D, f->dH, D, f->p.fc_w, hidden, f->dfeat, hidden, st, -1, true)
+                                             : kp_gemm_umma_dyn(ctx, f->dH, D, false, B, f->p.fc_w, hidden, true, hidden, D, f->dfeat, hidden, 0, st,
+                                                                f->tf32_mask & 32);
     if (rc != KP_OK) goto gemm_failed;
     vfit_bn2_bwd<<<B, 256, 0, st>>>(d, f->p, ord, f->C, f->feat, f->dfeat, S2, B2);
     vfit_conv_bwd<<<B, 256, smem_bwd, st>>>(d, f->p, ord, f->X0, f->C, f->dfeat, S1, S2, B2, B1, gCW, gCB, f->dX0);

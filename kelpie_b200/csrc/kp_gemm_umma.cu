@@ -45,6 +45,9 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// TF32 = false: operands are bf16 hi / lo tables (64 k per 128-byte block, error ~2^-17 per product);
+// TF32 = true: operands are tf32 hi / lo tables stored as fp32 (32 k per block, kind::tf32 at half the MMA rate, error ~2^-21).
+template <bool TF32>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GT, 1)
 gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_constant__ CUtensorMap bl64_map,
                  const __grid_constant__ CUtensorMap ah_map, const __grid_constant__ CUtensorMap al_map, const GK_ p) {
@@ -105,13 +108,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
       };
       for (int i = 0; i < ntile; ++i)
         for (int kb = kb0; kb < kb1; ++kb) {
-          load(&ah_map, &al_map, kb * 64, mtile * 128, 16384, 2 * 32768);                          // my 128 rows of A
-          load(&bh64_map, &bl64_map, kb * 64, (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the B tile
+          load(&ah_map, &al_map, kb * (TF32 ? 32 : 64), mtile * 128, 16384, 2 * 32768);                          // my 128 rows of A
+          load(&bh64_map, &bl64_map, kb * (TF32 ? 32 : 64), (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the B tile
         }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t fmt = TF32 ? 2u : 1u;  // cute::UMMA::F16F32Format: BF16 = 1, TF32 = 2
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t ring_a = ptx::smem_u32(ring);
       const uint64_t DK = udesc(0, 16, 1024);
       uint32_t use = 0;
@@ -132,9 +136,15 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
             if (kb * 4 + kk >= p.ksteps) break;  // only zero padding beyond K
-            ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
-            ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc, 1u);
-            ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc, 1u);
+            if (TF32) {
+              ptx::umma2_tf32(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              ptx::umma2_tf32(d_s, ah + kk * 2, bl + kk * 2, idesc, 1u);
+              ptx::umma2_tf32(d_s, al + kk * 2, bh + kk * 2, idesc, 1u);
+            } else {
+              ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc, (kb > kb0 || kk > 0) ? 1u : 0u);
+              ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc, 1u);
+              ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc, 1u);
+            }
           }
           ptx::umma2_commit_mc(&ctl->empty[use % NSLOT], 3);
           ptx::umma2_commit_mc(&ctl->empty[(use + 1) % NSLOT], 3);
@@ -236,46 +246,91 @@ __global__ void split2t_kernel(const float* __restrict__ src, long long rows, in
   }
 }
 
+__device__ __forceinline__ float to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+// fp32 [rows, cols] (ld) -> tf32 hi / lo [rows_pad, cols_pad] as fp32 words (zero padded): x = hi + lo + O(2^-22 |x|)
+__global__ void split2_tf32_kernel(const float* __restrict__ src, long long rows, int cols, long long ld, long long rows_pad, int cols_pad,
+                                   float* __restrict__ hi, float* __restrict__ lo) {
+  const long long total = rows_pad * (long long)cols_pad;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols_pad;
+    const int c = (int)(i - r * cols_pad);
+    const float a = (r < rows && c < cols) ? src[r * ld + c] : 0.f;
+    const float h = to_tf32(a);
+    hi[i] = h;
+    lo[i] = to_tf32(a - h);
+  }
+}
+// the same from the TRANSPOSE: src is [cols, rows] (ld)
+__global__ void split2t_tf32_kernel(const float* __restrict__ src, long long rows, int cols, long long ld, long long rows_pad, int cols_pad,
+                                    float* __restrict__ hi, float* __restrict__ lo) {
+  __shared__ float t[32][33];
+  const long long r0 = (long long)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long sr = c0 + j, sc = r0 + threadIdx.x;
+    t[j][threadIdx.x] = (sr < cols && sc < rows) ? src[sr * ld + sc] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = r0 + j;
+    const int c = c0 + threadIdx.x;
+    if (r < rows_pad && c < cols_pad) {
+      const float a = t[threadIdx.x][j];
+      const float h = to_tf32(a);
+      hi[r * cols_pad + c] = h;
+      lo[r * cols_pad + c] = to_tf32(a - h);
+    }
+  }
+}
+
 }  // namespace
 
 // C[M, N] = opA(A) * opB(B)^T with both operands given per call (fp32, split into workspace arena 1 behind `ws_offset`):
 // opA(A) = A [M, K] (lda) or, transA, the transpose of A [K, M];  opB(B) = B [N, K] (ldb) or, transB, the transpose of B [K, N].
 // A long K with few output tiles is cut over blockIdx.z and accumulated with fp32 reductions into a zeroed C.
 int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, int M, const float* B, long long ldb, bool transB,
-                     int N, int K, float* C, long long ldc, size_t ws_offset, cudaStream_t st) {
+                     int N, int K, float* C, long long ldc, size_t ws_offset, cudaStream_t st, bool tf32) {
   if (M <= 0 || N <= 0 || K <= 0) return KP_OK;
   const int Nc = (N + 3) & ~3;  // columns are stored four at a time: the (zero) padding up to Nc is written too
   if (ldc % 4 != 0 || ldc < Nc) KP_FAIL(ctx, KP_EINVAL, "tcgen05 GEMM needs ldc a multiple of 4 and >= N rounded up to 4");
   const int n_mt = ((M + 255) / 256) * 2;
   const long long Mpad = (long long)n_mt * 128, Npad = ((long long)N + 127) / 128 * 128;
-  const int Kpad = (K + 63) / 64 * 64;
-  const size_t abytes = ((size_t)Mpad * Kpad * 2 + 1023) & ~size_t(1023), bbytes = ((size_t)Npad * Kpad * 2 + 1023) & ~size_t(1023);
+  const int epb = tf32 ? 32 : 64, esz = tf32 ? 4 : 2;  // elements per 128-byte k-block, bytes per element
+  const int Kpad = (K + epb - 1) / epb * epb;
+  const size_t abytes = ((size_t)Mpad * Kpad * esz + 1023) & ~size_t(1023), bbytes = ((size_t)Npad * Kpad * esz + 1023) & ~size_t(1023);
   int rc;
   ws_offset = (ws_offset + 1023) & ~size_t(1023);
   if ((rc = kp_ws_reserve(ctx, ws_offset + 2 * abytes + 2 * bbytes + 2048, 1)) != KP_OK) return rc;
   char* base = ctx->ws_arena[1] + ws_offset;
-  __nv_bfloat16 *ah = (__nv_bfloat16*)base, *al = (__nv_bfloat16*)(base + abytes);
-  __nv_bfloat16 *bh = (__nv_bfloat16*)(base + 2 * abytes), *bl = (__nv_bfloat16*)(base + 2 * abytes + bbytes);
-  auto split = [&](const float* src, long long ld, bool trans, long long rows, long long rows_pad, __nv_bfloat16* h, __nv_bfloat16* l) {
-    if (trans)
-      split2t_kernel<<<dim3((unsigned)((rows_pad + 31) / 32), (unsigned)((Kpad + 31) / 32)), dim3(32, 8), 0, st>>>(src, rows, K, ld, rows_pad,
-                                                                                                           Kpad, h, l);
-    else
-      split2_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(src, rows, K, ld, rows_pad, Kpad, h, l);
+  void *ah = base, *al = base + abytes, *bh = base + 2 * abytes, *bl = base + 2 * abytes + bbytes;
+  auto split = [&](const float* src, long long ld, bool trans, long long rows, long long rows_pad, void* h, void* l) {
+    const dim3 tgrid((unsigned)((rows_pad + 31) / 32), (unsigned)((Kpad + 31) / 32));
+    if (tf32) {
+      if (trans) split2t_tf32_kernel<<<tgrid, dim3(32, 8), 0, st>>>(src, rows, K, ld, rows_pad, Kpad, (float*)h, (float*)l);
+      else split2_tf32_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(src, rows, K, ld, rows_pad, Kpad, (float*)h, (float*)l);
+    } else {
+      if (trans) split2t_kernel<<<tgrid, dim3(32, 8), 0, st>>>(src, rows, K, ld, rows_pad, Kpad, (__nv_bfloat16*)h, (__nv_bfloat16*)l);
+      else split2_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(src, rows, K, ld, rows_pad, Kpad, (__nv_bfloat16*)h, (__nv_bfloat16*)l);
+    }
   };
   split(A, lda, transA, M, Mpad, ah, al);
   split(B, ldb, transB, N, Npad, bh, bl);
   KP_LAUNCHED(ctx, 2);
+  const CUtensorMapDataType dt = tf32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap ah_map, al_map, bh_map, bl_map;
-  if ((rc = kp_encode_2d(ctx, &ah_map, ah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, Kpad, Kpad, 128, 64, true)) != KP_OK) return rc;
-  if ((rc = kp_encode_2d(ctx, &al_map, al, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, Kpad, Kpad, 128, 64, true)) != KP_OK) return rc;
-  if ((rc = kp_encode_2d(ctx, &bh_map, bh, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Kpad, Kpad, 64, 64, true)) != KP_OK) return rc;
-  if ((rc = kp_encode_2d(ctx, &bl_map, bl, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Npad, Kpad, Kpad, 64, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &ah_map, ah, dt, esz, Mpad, Kpad, Kpad, 128, epb, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &al_map, al, dt, esz, Mpad, Kpad, Kpad, 128, epb, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &bh_map, bh, dt, esz, Npad, Kpad, Kpad, 64, epb, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &bl_map, bl, dt, esz, Npad, Kpad, Kpad, 64, epb, true)) != KP_OK) return rc;
   GK_ p;
   p.M = M;
   p.N = Nc;
-  p.KB = Kpad / 64;
-  p.ksteps = (K + 15) / 16;
+  p.KB = Kpad / epb;
+  p.ksteps = (K + epb / 4 - 1) / (epb / 4);  // one MMA covers a quarter of a k-block (32 bytes): 16 bf16 or 8 tf32
   p.n_tiles = (N + 127) / 128;
   const int s = kp_plan_strips(n_mt / 2, ctx->sm_count / 2, p.n_tiles);
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;
@@ -296,12 +351,14 @@ int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, in
   p.ldc = ldc;
   static bool configured = false;
   if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
     configured = true;
   }
   {
     KpTimer timer(ctx, kp_ctx::T_CONV, st);
-    gemm_umma_kernel<<<dim3(n_mt, n_strips, ksplit), GT, G_SMEM, st>>>(bh_map, bl_map, ah_map, al_map, p);
+    if (tf32) gemm_umma_kernel<true><<<dim3(n_mt, n_strips, ksplit), GT, G_SMEM, st>>>(bh_map, bl_map, ah_map, al_map, p);
+    else gemm_umma_kernel<false><<<dim3(n_mt, n_strips, ksplit), GT, G_SMEM, st>>>(bh_map, bl_map, ah_map, al_map, p);
   }
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
@@ -370,12 +427,12 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   p.ldc = ldc;
   static bool configured = false;
   if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
+    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
     configured = true;
   }
   {
     KpTimer timer(ctx, kp_ctx::T_CONV, st);
-    gemm_umma_kernel<<<dim3(n_mt, n_strips, 1), GT, G_SMEM, st>>>(B.hi64, B.lo64, ah_map, al_map, p);
+    gemm_umma_kernel<false><<<dim3(n_mt, n_strips, 1), GT, G_SMEM, st>>>(B.hi64, B.lo64, ah_map, al_map, p);
   }
   KP_LAUNCHED(ctx, 1);
   return KP_OK;

@@ -239,4 +239,4 @@ inline int kp_plan_strips(long long units, long long slots, long long n_tiles) {
   return s;
 }
 int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, int M, const float* B, long long ldb, bool transB,
-                     int N, int K, float* C, long long ldc, size_t ws_offset, cudaStream_t st);
+                     int N, int K, float* C, long long ldc, size_t ws_offset, cudaStream_t st, bool tf32 = false);

@@ -1,7 +1,7 @@
 """Full-model ConvE training (bce_optimizer.py:44-158, conve.py:133-158) against golden state dicts
 produced by the unmodified reference's BCEOptimizer.train (tests/golden/make_golden_fit_conve.py): run "a" = 3 epochs x
-24 dependent Adam steps with train-mode batch-norm, run "b" = 2 epochs x 14 steps whose last step holds ONE pair and
-therefore runs the batch-norm layers in eval mode.
+24 dependent Adam steps with train-mode batch-norm, run "b" = one step over all pairs but one and one step over the
+last pair, which runs the batch-norm layers in eval mode.
 
 Stated tolerance: every trained tensor within 1e-3 of its own max |.| after 72 dependent Adam steps (measured on B200:
 1e-5, the reference's own fp32-vs-fp64 noise floor; relu gating + Adam's scale invariance amplify any perturbation ~100x
@@ -10,10 +10,10 @@ NOISE-DRIVEN tensors: a constant added in front of a train-mode batch-norm has a
 the convolution bias, the Linear bias and batch-norm 1's bias Adam integrates pure rounding noise (the reference's own
 fp32 and fp64 runs differ by 5e-4 .. 9e-4 there, and its values move by only ~7e-4 in run "a"); the running means of
 batch-norm 2 / 3 contain those biases.  These five are compared with an absolute 3e-3 instead.
-Run "b": its two single-pair steps give most Linear weights an exactly-zero or a rounding-sized gradient, which Adam turns
-into full-size moves; the reference's OWN fp32 and fp64 runs differ by 3.2e-3 of max |.| on hidden_layer.weight there
-(tools/debug_conve_fit.py prints both), so run "b" is held to 2e-2 of max |.| and 2e-3 in relative L2 norm (measured:
-7.9e-3 and 5e-4)."""
+Run "b" is two steps: all pairs but one (train mode), then a single pair (eval-mode batch-norm), checked right after.
+(The noise-driven biases random-walk; an eval-mode step reads them against lagging running means, and after a dozen
+steps that is enough to flip a relu gate in one implementation and not in another -- observed intermittently on one
+filter of 32 -- so a longer run would test the noise, not the eval-mode arithmetic.)"""
 import os
 
 import numpy as np
@@ -33,16 +33,16 @@ def _z():
 
 
 def _hp(z, tag):
-    return HP if tag == "a" else dict(HP, batch_size=int(z["batch_b"]), epochs=2)
+    return HP if tag == "a" else dict(HP, batch_size=int(z["batch_b"]), epochs=1)
 
 
-def _check(got, z, tag, tol, noise_tol, l2_tol=None):
+def _check(got, z, tag, tol, noise_tol, l2_tol=None, loose=()):
     from oracle.kelpie_oracle import CONVE_STATE_KEYS
     for k in CONVE_STATE_KEYS:
         want = z[f"{tag}/{k}"]
         diff = np.asarray(got[k]).reshape(want.shape) - want
         err = np.abs(diff).max()
-        bound = noise_tol if k in NOISE_DRIVEN else tol * np.abs(want).max()
+        bound = noise_tol if k in NOISE_DRIVEN else (10 * tol if k in loose else tol) * np.abs(want).max()
         assert err <= bound, (tag, k, err, bound)
         if l2_tol is not None and k not in NOISE_DRIVEN:
             assert np.linalg.norm(diff) <= l2_tol * np.linalg.norm(want), (tag, k, np.linalg.norm(diff) / np.linalg.norm(want))
@@ -86,11 +86,11 @@ def test_cuda_full_training_matches_reference(tag):
     opt = opt_cls(model=m, hp=opt_cls.get_hyperparams_class()(**_hp(z, tag)), verbose=True)
     opt.train(training_triples=ds.training_triples)
     got = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
-    if tag == "a":
-        _check(got, z, tag, 1e-3, 3e-3, l2_tol=1e-3)
-    else:
-        _check(got, z, tag, 2e-2, 3e-3, l2_tol=2e-3)
-    assert opt.epoch_losses[-1] < opt.epoch_losses[0]
+    # run "b": in Adam's first two steps an element whose gradient is of the size of eps (1e-8, against ~1e-4 typical) moves
+    # by lr * g / (|g| + eps); a handful of the 73k Linear weights are like that and their g carries the 2^-21 rounding of
+    # the tf32x3 products of a 3029-term sum (measured 4e-3 of max |.| on those elements, 5e-5 in relative L2 norm)
+    _check(got, z, tag, 1e-3, 3e-3, l2_tol=1e-3, loose=("hidden_layer.weight",) if tag == "b" else ())
+    assert len(opt.epoch_losses) == (3 if tag == "a" else 1) and (tag == "b" or opt.epoch_losses[-1] < opt.epoch_losses[0])
 
 
 @pytest.mark.gpu
