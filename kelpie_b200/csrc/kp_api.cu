@@ -167,6 +167,14 @@ int kp_encode_2d_f32(kp_ctx* ctx, CUtensorMap* map, const float* base, int64_t r
 
 int kp_encode_2d(kp_ctx* ctx, CUtensorMap* map, const void* base, CUtensorMapDataType dtype, int elem_bytes,
                  int64_t rows, int64_t cols, int64_t ld_floats, int box_rows, int box_cols, bool swizzle128) {
+  const kp_ctx::TmapKey key((const void*)base, (int)dtype * 16 + elem_bytes, rows, cols, ld_floats, box_rows, box_cols, swizzle128);
+  if (ctx) {
+    auto it = ctx->tmaps.find(key);
+    if (it != ctx->tmaps.end()) {
+      *map = it->second;
+      return KP_OK;
+    }
+  }
   encode_tiled_fn enc = get_encode();
   if (!enc) KP_FAIL(ctx, KP_ECUDA, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -180,6 +188,10 @@ int kp_encode_2d(kp_ctx* ctx, CUtensorMap* map, const void* base, CUtensorMapDat
   if (r != CUDA_SUCCESS)
     KP_FAIL(ctx, KP_ECUDA, "cuTensorMapEncodeTiled failed (%d) rows=%lld cols=%lld ld=%lld", (int)r,
             (long long)rows, (long long)cols, (long long)ld_floats);
+  if (ctx) {
+    if (ctx->tmaps.size() >= 512) ctx->tmaps.clear();
+    ctx->tmaps.emplace(key, *map);
+  }
   return KP_OK;
 }
 

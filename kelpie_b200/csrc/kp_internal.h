@@ -4,7 +4,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/kelpie_b200.h"
@@ -61,6 +63,10 @@ struct kp_ctx {
   size_t ws_bytes = 0;
   char* ws_arena[2] = {nullptr, nullptr};
   size_t ws_arena_bytes[2] = {0, 0};
+
+  // tensor maps depend only on (base, type, shape, pitch, box): encoded once per distinct key (kp_encode_2d)
+  typedef std::tuple<const void*, int, int64_t, int64_t, int64_t, int, int, bool> TmapKey;
+  std::map<TmapKey, CUtensorMap> tmaps;
 
   int64_t launches = 0;
   int64_t rank_rechecks = 0;  // pairs the tensor-core rank pass handed to the exact re-check so far
