@@ -17,6 +17,16 @@
 //
 // Counters per query (as kp_pass.cu): strictly better / tied / tied with a smaller id, over entities
 // that are neither filtered nor the target, and the best other score.
+//
+// TransE with the L2 norm (transe.py:48-65, a minimiser) runs through the same kernel: the epilogue turns
+// the tensor-core dot product into the negated squared distance  x = 2 q.E_j - |q|^2 - |E_j|^2, which
+// differs from MINUS the exact pass's fp32 chain  sum_k fl(q_k - E_jk)^2  by at most
+//     margin(q, j) = kappa2 * (|q|^2 + |E_j|^2) ,   kappa2 = kappa + (4 D + 64) * 2^-24
+// (2 kappa |q||E_j| <= kappa (|q|^2 + |E_j|^2) from the dot product; (D + 8) 2^-24 relative from each
+// fp32 norm, 3 ulp from the epilogue arithmetic, 2 (D + 3) 2^-24 from the exact chain's own rounding).
+// The "activation" is then f(x) = -sqrtf(-x) (monotone, sqrtf correctly rounded), the target -t, and
+// "strictly better" means f(x) > -t exactly as for the maximisers; undecided pairs are re-evaluated
+// with the exact pass's sequential  d = q_k - E_jk; acc = fma(d, d, acc); sqrtf(acc).
 #include <cuda_bf16.h>
 
 #include "kp_internal.h"
@@ -37,9 +47,11 @@ struct RCtl {
 };
 constexpr size_t R_SMEM = (size_t)NSLOT * SLOT + sizeof(RCtl) + 1024;
 
+constexpr int ACT_NEGSQRT = 2;  // internal: f(x) = -sqrtf(-x) on x <= 0 (L2 distance as a maximiser)
+
 struct RK {
   int Qn, N, D, KB, n_tiles, tiles_per_strip;
-  float kappa;
+  float kappa;             // DOT: kappa; L2: kappa2
   const float* enorm;      // [Npad]
   const float* qnorm;      // [Qpad]
   const float* xlo;        // [Qpad] largest pre-activation score that ranks strictly below the target
@@ -65,6 +77,7 @@ __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, ui
   return d;
 }
 
+template <bool L2>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(RT, 1)
 rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_constant__ CUtensorMap el64_map,
                  const __grid_constant__ CUtensorMap qh_map, const __grid_constant__ CUtensorMap ql_map, const RK p) {
@@ -171,7 +184,9 @@ rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_cons
     const bool live = q < p.Qn;
     const uint32_t s_free_leader0 = ptx::mapa_u32(ptx::smem_u32(&ctl->s_free[0]), 0);
     const float xlo = live ? p.xlo[q] : INFINITY, xhi = live ? p.xhi[q] : INFINITY;
-    const float qm = live ? p.qnorm[q] * p.kappa : 0.f;
+    const float qn = live ? p.qnorm[q] : 0.f;
+    const float qm = qn * p.kappa;  // DOT margin factor
+    const float qn2 = qn * qn;      // L2
     const int tgt = live ? p.tgt_ent[q] : -1;
     long long cur = 0, fend = 0;
     if (live) {
@@ -221,8 +236,16 @@ rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_cons
         uint32_t unsure = 0;
 #pragma unroll
         for (int c = 0; c < 32; ++c) {
-          const float s = __uint_as_float(r[c]);
-          const float m = qm * ctl->enorm[sb][c0 + c];
+          float s = __uint_as_float(r[c]);
+          float m;
+          if (L2) {
+            const float en = ctl->enorm[sb][c0 + c];
+            const float nn = __fmaf_rn(en, en, qn2);
+            s = __fmaf_rn(2.f, s, -nn);
+            m = p.kappa * nn;
+          } else {
+            m = qm * ctl->enorm[sb][c0 + c];
+          }
           const bool valid = !((mw >> c) & 1u);
           const bool above = (s - m >= xhi), below = (s + m <= xlo);
           strict += (valid && above);
@@ -250,7 +273,11 @@ rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_cons
   if (warp == 1) ptx::tmem_dealloc2(tm, 256);
 }
 
-__device__ __forceinline__ float act_apply(int act, float x) { return act == KP_ACT_SIGMOID ? 1.f / (1.f + expf(-x)) : x; }
+__device__ __forceinline__ float act_apply(int act, float x) {
+  if (act == KP_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  if (act == ACT_NEGSQRT) return -sqrtf(-x);
+  return x;
+}
 
 // Per query: |q|_2 and the pre-activation thresholds.  target[q] is the (activated) target score the
 // exact pass would compare with; NaN (invalid triple) -> nothing is ever better or tied.
@@ -272,14 +299,15 @@ __global__ void rank_prepare(int Q, int Qpad, int D, int act, const float* __res
   const float none = __int_as_float(0x7fc00000);
   float lo = INFINITY, hi = none;  // padding rows / invalid target: everything certainly below
   if (q < Q) {
-    const float t = target[q];
+    const float t = (act == ACT_NEGSQRT) ? -target[q] : target[q];
+    const float top = (act == ACT_NEGSQRT) ? 0.f : INFINITY;  // largest pre-activation value of the domain
     if (t == t) {
       const int slack = (act == KP_ACT_SIGMOID) ? 4 : 0;
       const float tm = kp_unord(kp_ord(t) - slack), tp = kp_unord(kp_ord(t) + slack);
-      const uint32_t a0 = kp_ord(-INFINITY), b0 = kp_ord(INFINITY);
+      const uint32_t a0 = kp_ord(-INFINITY), b0 = kp_ord(top);
       if (!(act_apply(act, -INFINITY) < tm)) {
         lo = none;
-      } else if (act_apply(act, INFINITY) < tm) {
+      } else if (act_apply(act, top) < tm) {
         lo = INFINITY;
       } else {
         uint32_t l = a0, h = b0;  // f(l) < t-, f(h) >= t-
@@ -289,7 +317,7 @@ __global__ void rank_prepare(int Q, int Qpad, int D, int act, const float* __res
         }
         lo = kp_unord(l);
       }
-      if (!(act_apply(act, INFINITY) > tp)) {
+      if (!(act_apply(act, top) > tp)) {
         hi = none;
       } else if (act_apply(act, -INFINITY) > tp) {
         hi = -INFINITY;
@@ -317,15 +345,30 @@ __global__ void rank_recheck(unsigned long long n, const int2* __restrict__ pair
     const float4* a = reinterpret_cast<const float4*>(qmat + (size_t)pr.x * D);
     const float4* b = reinterpret_cast<const float4*>(ent + (size_t)pr.y * D);
     float acc = 0.f;
-    for (int k = 0; k < D / 4; ++k) {
-      const float4 x = a[k], y = b[k];
-      acc = __fmaf_rn(x.x, y.x, acc);
-      acc = __fmaf_rn(x.y, y.y, acc);
-      acc = __fmaf_rn(x.z, y.z, acc);
-      acc = __fmaf_rn(x.w, y.w, acc);
+    if (act == ACT_NEGSQRT) {  // kp_pass.cu accum<KP_OP_L2>
+      for (int k = 0; k < D / 4; ++k) {
+        const float4 x = a[k], y = b[k];
+        float d = __fsub_rn(x.x, y.x);
+        acc = __fmaf_rn(d, d, acc);
+        d = __fsub_rn(x.y, y.y);
+        acc = __fmaf_rn(d, d, acc);
+        d = __fsub_rn(x.z, y.z);
+        acc = __fmaf_rn(d, d, acc);
+        d = __fsub_rn(x.w, y.w);
+        acc = __fmaf_rn(d, d, acc);
+      }
+      acc = -acc;
+    } else {
+      for (int k = 0; k < D / 4; ++k) {
+        const float4 x = a[k], y = b[k];
+        acc = __fmaf_rn(x.x, y.x, acc);
+        acc = __fmaf_rn(x.y, y.y, acc);
+        acc = __fmaf_rn(x.z, y.z, acc);
+        acc = __fmaf_rn(x.w, y.w, acc);
+      }
     }
-    const float sc = act_apply(act, acc);
-    const float t = target[pr.x];
+    const float sc = act_apply(act, acc);  // L2: minus the distance, compared with minus the target's
+    const float t = (act == ACT_NEGSQRT) ? -target[pr.x] : target[pr.x];
     if (sc > t) atomicAdd(&cnt[pr.x * 4 + 0], 1);
     if (sc == t) {
       atomicAdd(&cnt[pr.x * 4 + 1], 1);
@@ -340,23 +383,28 @@ __global__ void rank_best_finish(int Q, int act, const uint32_t* __restrict__ be
                                  uint32_t* __restrict__ best) {
   const int q = blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= Q) return;
-  const float pre = kp_unord(best_pre[q]);
+  float pre = kp_unord(best_pre[q]);
+  if (act == ACT_NEGSQRT) pre = fminf(pre, 0.f);  // a tensor-core estimate of a tiny squared distance may come out negative
   const float a = (pre == -INFINITY || pre != pre) ? -INFINITY : act_apply(act, pre);  // no valid entity: as the exact pass
   const float b = best_act[q] ? kp_unord(best_act[q]) : -INFINITY;
-  best[q] = kp_ord(fmaxf(a, b));
+  const float m = fmaxf(a, b);
+  best[q] = kp_ord(act == ACT_NEGSQRT ? -m : m);  // L2: back to a distance (the caller keeps the minimum)
 }
 
 }  // namespace
 
 bool kp_rank_umma_usable(kp_ctx* ctx, const kp_pass_args& a) {
-  return ctx->umma_rank != 0 && !ctx->force_simt && a.rank && !a.minimize && a.op == KP_OP_DOT && a.Qn >= 128 && ctx->D <= 512 &&
-         ctx->D % 4 == 0;
+  const bool dot = a.op == KP_OP_DOT && !a.minimize;
+  const bool l2 = a.op == KP_OP_L2 && a.minimize && a.act == KP_ACT_NONE;
+  return ctx->umma_rank != 0 && !ctx->force_simt && a.rank && (dot || l2) && a.Qn >= 128 && ctx->D <= 512 && ctx->D % 4 == 0;
 }
 
 int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   int rc;
   if ((rc = kp_umma_tables(ctx, st)) != KP_OK) return rc;
   const int Q = a.Qn, D = ctx->D;
+  const bool l2 = a.op == KP_OP_L2;
+  const int act = l2 ? ACT_NEGSQRT : a.act;
   const int n_qt = ((Q + 255) / 256) * 2;  // pairs of query tiles
   const long long Qpad = (long long)n_qt * 128;
   CUtensorMap qh_map, ql_map;
@@ -377,7 +425,7 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   unsigned long long* n_pairs = ws.take<unsigned long long>(2);
   int2* pairs = ws.take<int2>(cap);
 
-  rank_prepare<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(Q, (int)Qpad, D, a.act, a.qmat, a.target, qnorm, xlo, xhi);
+  rank_prepare<<<(unsigned)((Qpad + 7) / 8), 256, 0, st>>>(Q, (int)Qpad, D, act, a.qmat, a.target, qnorm, xlo, xhi);
   KP_LAUNCHED(ctx, 1);
   KP_CUDA(ctx, cudaMemsetAsync(best_pre, 0, (size_t)Q * 4, st));
   KP_CUDA(ctx, cudaMemsetAsync(best_act, 0, (size_t)Q * 4, st));
@@ -393,6 +441,7 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
   p.kappa = ldexpf(1.f, -16) + (float)D * ldexpf(1.f, -22);
+  if (l2) p.kappa += (float)(4 * D + 64) * ldexpf(1.f, -24);
   p.enorm = ctx->um.enorm;
   p.qnorm = qnorm;
   p.xlo = xlo;
@@ -408,12 +457,16 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   p.cap_pairs = cap;
   static bool configured = false;
   if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
+    KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
+    KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
     configured = true;
   }
   {
     KpTimer timer(ctx, kp_ctx::T_PASS, st);
-    rank_umma_kernel<<<dim3(n_qt, n_strips, 1), RT, R_SMEM, st>>>(ctx->um.eh64_map, ctx->um.el64_map, qh_map, ql_map, p);
+    if (l2)
+      rank_umma_kernel<true><<<dim3(n_qt, n_strips, 1), RT, R_SMEM, st>>>(ctx->um.eh64_map, ctx->um.el64_map, qh_map, ql_map, p);
+    else
+      rank_umma_kernel<false><<<dim3(n_qt, n_strips, 1), RT, R_SMEM, st>>>(ctx->um.eh64_map, ctx->um.el64_map, qh_map, ql_map, p);
   }
   KP_LAUNCHED(ctx, 1);
   // the list length decides the re-check grid (and whether the list overflowed): one small synchronous read
@@ -429,10 +482,10 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   if (n > 0) {
     unsigned blocks = (unsigned)((n + 255) / 256);
     if (blocks > (unsigned)ctx->sm_count * 16) blocks = (unsigned)ctx->sm_count * 16;
-    rank_recheck<<<blocks, 256, 0, st>>>(n, pairs, D, a.act, a.qmat, ctx->ent, a.target, a.tgt_ent, a.cnt, best_act);
+    rank_recheck<<<blocks, 256, 0, st>>>(n, pairs, D, act, a.qmat, ctx->ent, a.target, a.tgt_ent, a.cnt, best_act);
     KP_LAUNCHED(ctx, 1);
   }
-  rank_best_finish<<<(Q + 255) / 256, 256, 0, st>>>(Q, a.act, best_pre, best_act, a.best);
+  rank_best_finish<<<(Q + 255) / 256, 256, 0, st>>>(Q, act, best_pre, best_act, a.best);
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
 }

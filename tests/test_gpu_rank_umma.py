@@ -42,7 +42,7 @@ def _both(ctx, triples, mode, mimic, off, ids):
     return out
 
 
-def _assert_same(out, Q, N, max_recheck_frac):
+def _assert_same(out, Q, N, max_recheck_frac, best_tol=None):
     ts1, bs1, rk1, cn1, n1 = out[1]
     ts0, bs0, rk0, cn0, n0 = out[0]
     assert n0 == 0
@@ -51,7 +51,10 @@ def _assert_same(out, Q, N, max_recheck_frac):
     assert np.array_equal(ts1, ts0)
     fin = np.isfinite(bs0)
     assert np.array_equal(np.isfinite(bs1), fin)
-    assert np.abs(bs1[fin] - bs0[fin]).max() <= 1e-4 * max(1.0, np.abs(bs0[fin]).max())
+    if best_tol is None:
+        assert np.abs(bs1[fin] - bs0[fin]).max() <= 1e-4 * max(1.0, np.abs(bs0[fin]).max())
+    else:  # L2: the tensor-core estimate of the best distance is accurate in the SQUARED domain
+        assert np.abs(bs1[fin].astype(np.float64) ** 2 - bs0[fin].astype(np.float64) ** 2).max() <= best_tol
     assert n1 <= max_recheck_frac * Q * N, f"{n1} re-checks for {Q} x {N} pairs"
 
 
@@ -107,4 +110,47 @@ def test_rank_full_size_matches_exact_pass():
     off, ids = _filters(rng, Q, N, triples[:, 2])
     out = _both(ctx, triples, 2, None, off, ids)
     _assert_same(out, Q, N, 0.01)
+    ctx.close()
+
+
+@pytest.mark.parametrize("D,N,Q", [(256, 5003, 700), (128, 9001, 300), (200, 3000, 129)])
+@pytest.mark.parametrize("mode", [0, 2])
+def test_transe_l2_rank_identical(D, N, Q, mode):
+    """TransE with the L2 norm (a minimiser: transe.py:48-65) through the tensor-core pass: squared-distance
+    margins, exact re-check with the exact pass's chain.  Duplicate rows (exact ties), near-duplicates (distances
+    that differ in the last bits), targets at distance ~0 and mimic heads."""
+    from kelpie_b200 import runtime
+    rng = np.random.default_rng(D + N + Q + mode)
+    ent = (rng.standard_normal((N, D)) * 0.3).astype(np.float32)
+    ent[N // 2: N // 2 + 40] = ent[7:47]                                             # exact ties
+    ent[N // 3: N // 3 + 40] = ent[7:47] * np.float32(1 + 2e-7)                      # near ties
+    rel = (rng.standard_normal((14, D)) * 0.3).astype(np.float32)
+    rel[3] = 0.0                                                                     # (h, 3, h): distance exactly 0
+    ctx = runtime.Context("TransE", ent, rel, norm=2)
+    triples = _queries(rng, Q, N, 14, mimic_every=5)
+    triples[1::7, 2] = 10  # targets among the duplicated rows
+    triples[2::11, 1] = 3
+    triples[2::11, 2] = np.where(triples[2::11, 0] == N, 5, triples[2::11, 0])
+    mimic = (rng.standard_normal((Q, D)) * 0.3).astype(np.float32)
+    off, ids = _filters(rng, Q, N, triples[:, 2])
+    out = _both(ctx, triples, mode, mimic, off, ids)
+    _assert_same(out, Q, N, 0.05, best_tol=2e-3 * 2 * D * 0.09)
+    assert out[1][4] > 0          # the tensor-core pass ran (it reports its re-checks)
+    assert out[1][3][:, 1].sum() > 0  # ties exist
+    ctx.close()
+
+
+def test_transe_l2_rank_dbpedia50_shape():
+    """BASELINE configs[0] shape (24 620 x 256, 4097 queries with their own mimic head): ranks identical, few re-checks."""
+    from kelpie_b200 import runtime
+    rng = np.random.default_rng(11)
+    N, D, Q = 24620, 256, 4097
+    ent = (rng.standard_normal((N, D)) * (2.0 / (N + D)) ** 0.5 * 30).astype(np.float32)
+    rel = (rng.standard_normal((702, D)) * 0.05).astype(np.float32)
+    ctx = runtime.Context("TransE", ent, rel, norm=2)
+    triples = _queries(rng, Q, N, 702, mimic_every=1)
+    mimic = (rng.standard_normal((Q, D)) * 0.1).astype(np.float32)
+    off, ids = _filters(rng, Q, N, triples[:, 2])
+    out = _both(ctx, triples, 0, mimic, off, ids)
+    _assert_same(out, Q, N, 0.02, best_tol=2e-2)
     ctx.close()
