@@ -120,7 +120,7 @@ def make_batch(cfg, D, C, seed):
         jobs.append(facts)
         n_f = min(512, int(rng.zipf(2.0)))  # filter list: Zipf lengths (mean ~2, capped at 512)
         filters.append(np.unique(rng.integers(0, N, size=n_f)).astype(np.int32))
-    arrs = batch.arrays()
+    arrs = batch.arrays(compact=not os.environ.get("KP_BENCH_FULL_TABLES"))  # TransE: compact index tables (kelpie_b200.h)
     p, o = int(rng.integers(0, R)), int(rng.integers(0, N))
     triples = np.tile(np.array([[N, p, o]], dtype=np.int32), (len(jobs), 1))
     flt_off = np.zeros(len(jobs) + 1, dtype=np.int64)
@@ -132,11 +132,10 @@ def make_batch(cfg, D, C, seed):
 def algorithmic_work(cfg, D, arrs):
     """executed algorithmic flops / bytes of ONE launch of the dominant kernel."""
     kind, N = cfg["kind"], cfg["N"]
-    pos = arrs["pos"]
     if kind == "TransE":  # rank pass: table read once per 64 queries (HBM) / 3 Q N D flops
         Q = len(arrs["init_rows"])
         return dict(bound="hbm", units=((Q + 63) // 64) * N * D * 4.0, what="pass")
-    a_rows = int((pos[:, 0] == N).sum())  # rows / pairs whose lhs is the mimic, per step
+    a_rows = int((arrs["pos"][:, 0] == N).sum())  # rows / pairs whose lhs is the mimic, per step
     return dict(bound="tensor", units=4.0 * a_rows * N * D, what="flash")
 
 
@@ -261,8 +260,9 @@ def main():
     mode = runtime.RANK_ENGINE_MIN if kind == "TransE" else runtime.RANK_ENGINE_MAX
     work = algorithmic_work(cfg, D, arrs)
     dtypes = dict(init_rows=torch.float32, row_off=torch.int64, rows_per_epoch=torch.int32, pos=torch.int32,
-                  neg=torch.int32, pos_off=torch.int64, pos_ids=torch.int32)
-    host = {k: v for k, v in arrs.items() if k != "static_epochs"}
+                  neg=torch.int32, pos_off=torch.int64, pos_ids=torch.int32, fact_off=torch.int64, facts=torch.int32,
+                  pos_idx=torch.uint16, neg_code=torch.int32)
+    host = {k: v for k, v in arrs.items() if k != "static_epochs" and v is not None}
     h2d = sum(v.nbytes for v in host.values()) + triples.nbytes + flt_off.nbytes + flt_ids.nbytes
     max_rows, total_rows = int(arrs["rows_per_epoch"].max()), int(arrs["row_off"][-1])
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=device) if ent.numel() * 4 < (200 << 20) else None

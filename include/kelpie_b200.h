@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 1
+#define KP_ABI_VERSION 2
 
 enum kp_status {
   KP_OK = 0,
@@ -120,6 +120,15 @@ typedef struct kp_pt_batch {
   const float* init_rows;        /* [C, D] */
   float* out_rows;               /* [C, D] */
   uint64_t dropout_seed;         /* ConvE with dropout > 0 */
+  /* TransE, optional (ABI 2): compact index tables, 6 instead of 24 bytes per training row over PCIe.  When pos_idx
+   * is non-NULL, pos / neg are ignored: candidate c's distinct rows ("triples + inverse triples",
+   * pairwise_ranking_optimizer.py:64-65) are facts[fact_off[c] .. fact_off[c+1]) and training row i (same row_off /
+   * rows_per_epoch / epoch-major layout) is the positive facts[fact_off[c] + pos_idx[i]] with, as its negative
+   * (:171-195), the head (bit 31 of neg_code[i] set) or the tail (clear) replaced by entity neg_code[i] & 0x7fffffff. */
+  const int64_t* fact_off;       /* [C+1] */
+  const int32_t* facts;          /* [fact_off[C], 3] */
+  const uint16_t* pos_idx;       /* [rows] */
+  const int32_t* neg_code;       /* [rows] */
 } kp_pt_batch;
 
 /* Queries of one scoring / ranking call: Q triples (s,p,o) int32 [Q,3] on the device.

@@ -26,6 +26,11 @@ struct TrainK {
   const int32_t* neg;
   const float* init;
   float* out;
+  const float2* adam;  // [epochs * steps per epoch] bias-correction table
+  const int64_t* fact_off;  // compact tables (kp_pt_batch)
+  const int32_t* facts;
+  const uint16_t* pos_idx;
+  const int32_t* neg_code;
   kp_hp hp;
 };
 
@@ -39,7 +44,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 __device__ __forceinline__ float sgn(float x) { return (x > 0.f) ? 1.f : ((x < 0.f) ? -1.f : 0.f); }
 
-template <int VPL>  // float4 vectors per lane; D <= 128 * VPL
+// Adam's bias corrections depend on the step number only: step_size = lr / (1 - beta1^t), sqrt(1 - beta2^t),
+// evaluated in double as torch does on the host (optim/adam.py _single_tensor_adam).  One table for the whole batch
+// instead of two double-precision pow() per thread and step inside the training kernel.
+__global__ void adam_table_kernel(int steps, float lr, float beta1, float beta2, float2* __restrict__ tab) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= steps) return;
+  const double bc1 = 1.0 - pow((double)beta1, (double)(t + 1));
+  const double bc2 = 1.0 - pow((double)beta2, (double)(t + 1));
+  tab[t] = make_float2((float)((double)lr / bc1), (float)sqrt(bc2));
+}
+
+// VPL: float4 vectors per lane (D <= 128 * VPL).  U: rows a warp has in flight at once (independent gathers).
+// CP: compact index tables (kp_pt_batch.pos_idx / neg_code / facts) instead of pos / neg.
+template <int VPL, int U, bool CP>
 __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p) {
   extern __shared__ float sm[];
   const int D = p.D;
@@ -53,6 +71,7 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n = p.rows_per_epoch[c];
   const int64_t base0 = p.row_off[c];
+  const int32_t* facts = CP ? p.facts + p.fact_off[c] * 3 : nullptr;
   for (int k = tid; k < D; k += TT_THREADS) {
     eM[k] = p.init[(size_t)c * D + k];
     am[k] = 0.f;
@@ -62,121 +81,206 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
 
   const int M = p.N;
   const int bs = p.hp.batch_size;
-  long long step = 0;
-  for (int ep = 0; ep < p.hp.epochs; ++ep) {
-    const int64_t ebase = base0 + (p.static_epochs ? 0 : (int64_t)ep * n);
-    for (int b0 = 0; b0 < n; b0 += bs) {
-      const int B = min(bs, n - b0);
-      float4 g[VPL];
+  const int spe = (n + bs - 1) / bs;  // steps per epoch
+  const long long n_steps = (long long)p.hp.epochs * spe;
+
+  // The index rows of a step do not depend on the mimic row: they are fetched one step ahead, LPS lanes per row
+  // (full tables: pos h, r, t, neg h, r, t; compact: the positive fact's h, r, t and the corruption code).
+  constexpr int LPS = CP ? 4 : 6;
+  constexpr int PF = 32 / LPS;
+  auto step_base = [&](long long s, int& b0) -> int64_t {
+    const int ep = (int)(s / spe);
+    b0 = (int)(s % spe) * bs;
+    return base0 + (p.static_epochs ? 0 : (int64_t)ep * n) + b0;
+  };
+  auto prefetch = [&](long long s) -> int {
+    if (s >= n_steps || lane >= LPS * PF) return 0;
+    int b0;
+    const int64_t rb = step_base(s, b0);
+    const int B = min(bs, n - b0);
+    const int i = warp + TT_WARPS * (lane / LPS), k = lane % LPS;
+    if (i >= B) return 0;
+    if (CP) return (k == 3) ? p.neg_code[rb + i] : facts[(int)p.pos_idx[rb + i] * 3 + k];
+    return (k < 3 ? p.pos : p.neg)[(rb + i) * 3 + (k % 3)];
+  };
+  int pf = prefetch(0);
+
+  for (long long step = 0; step < n_steps; ++step) {
+    int b0;
+    const int64_t rb = step_base(step, b0);
+    const int B = min(bs, n - b0);
+    float4 g[VPL];
 #pragma unroll
-      for (int v = 0; v < VPL; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
-      int cnt = 0;
-      for (int i = warp; i < B; i += TT_WARPS) {
-        const int32_t* pr = p.pos + (ebase + b0 + i) * 3;
-        const int32_t* nr = p.neg + (ebase + b0 + i) * 3;
-        const int h = pr[0], r = pr[1], t = pr[2], h2 = nr[0], t2 = nr[2];
-        const float* ph = (h == M) ? eM : p.ent + (size_t)h * D;
-        const float* pt = (t == M) ? eM : p.ent + (size_t)t * D;
-        const float* ph2 = (h2 == M) ? eM : p.ent + (size_t)h2 * D;
-        const float* pt2 = (t2 == M) ? eM : p.ent + (size_t)t2 * D;
-        const float* prl = p.rel + (size_t)r * D;
-        float4 dp[VPL], dn[VPL];
-        float sp = 0.f, sn = 0.f;
+    for (int v = 0; v < VPL; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+    int cnt = 0;
+    int slot = 0;
+    for (int i = warp; i < B; i += U * TT_WARPS, slot += U) {
+      int h[U], r[U], t[U], h2[U], t2[U];
+      bool valid[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int iu = i + u * TT_WARPS;
+        valid[u] = iu < B;  // warp-uniform
+        if (slot + u < PF) {
+          const int l0 = LPS * (slot + u);
+          h[u] = __shfl_sync(0xffffffffu, pf, l0 + 0);
+          r[u] = __shfl_sync(0xffffffffu, pf, l0 + 1);
+          t[u] = __shfl_sync(0xffffffffu, pf, l0 + 2);
+          if (CP) {
+            const int code = __shfl_sync(0xffffffffu, pf, l0 + 3);
+            h2[u] = (code < 0) ? (code & 0x7fffffff) : h[u];
+            t2[u] = (code < 0) ? t[u] : code;
+          } else {
+            h2[u] = __shfl_sync(0xffffffffu, pf, l0 + 3);
+            t2[u] = __shfl_sync(0xffffffffu, pf, l0 + 5);
+          }
+        } else if (valid[u]) {
+          if (CP) {
+            const int32_t* f = facts + (int)p.pos_idx[rb + iu] * 3;
+            const int code = p.neg_code[rb + iu];
+            h[u] = f[0], r[u] = f[1], t[u] = f[2];
+            h2[u] = (code < 0) ? (code & 0x7fffffff) : h[u];
+            t2[u] = (code < 0) ? t[u] : code;
+          } else {
+            const int32_t* pr = p.pos + (rb + iu) * 3;
+            const int32_t* nr = p.neg + (rb + iu) * 3;
+            h[u] = pr[0], r[u] = pr[1], t[u] = pr[2], h2[u] = nr[0], t2[u] = nr[2];
+          }
+        }
+        if (!valid[u]) h[u] = t[u] = h2[u] = t2[u] = M, r[u] = 0;  // harmless addresses; contributions masked below
+      }
+      float4 dp[U][VPL], dn[U][VPL];
+      float sp[U], sn[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float* ph = (h[u] == M) ? eM : p.ent + (size_t)h[u] * D;
+        const float* pt = (t[u] == M) ? eM : p.ent + (size_t)t[u] * D;
+        const float* ph2 = (h2[u] == M) ? eM : p.ent + (size_t)h2[u] * D;
+        const float* pt2 = (t2[u] == M) ? eM : p.ent + (size_t)t2[u] * D;
+        const float* prl = p.rel + (size_t)r[u] * D;
+        sp[u] = sn[u] = 0.f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           const int k = (v * 32 + lane) * 4;
-          dp[v] = dn[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+          dp[u][v] = dn[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
           if (k < D) {
             const float4 a = ld4(ph + k), rr = ld4(prl + k), b = ld4(pt + k);
             const float4 a2 = ld4(ph2 + k), b2 = ld4(pt2 + k);
-            dp[v].x = __fsub_rn(__fadd_rn(a.x, rr.x), b.x);
-            dp[v].y = __fsub_rn(__fadd_rn(a.y, rr.y), b.y);
-            dp[v].z = __fsub_rn(__fadd_rn(a.z, rr.z), b.z);
-            dp[v].w = __fsub_rn(__fadd_rn(a.w, rr.w), b.w);
-            dn[v].x = __fsub_rn(__fadd_rn(a2.x, rr.x), b2.x);
-            dn[v].y = __fsub_rn(__fadd_rn(a2.y, rr.y), b2.y);
-            dn[v].z = __fsub_rn(__fadd_rn(a2.z, rr.z), b2.z);
-            dn[v].w = __fsub_rn(__fadd_rn(a2.w, rr.w), b2.w);
+            float4& x = dp[u][v];
+            float4& y = dn[u][v];
+            x.x = __fsub_rn(__fadd_rn(a.x, rr.x), b.x);
+            x.y = __fsub_rn(__fadd_rn(a.y, rr.y), b.y);
+            x.z = __fsub_rn(__fadd_rn(a.z, rr.z), b.z);
+            x.w = __fsub_rn(__fadd_rn(a.w, rr.w), b.w);
+            y.x = __fsub_rn(__fadd_rn(a2.x, rr.x), b2.x);
+            y.y = __fsub_rn(__fadd_rn(a2.y, rr.y), b2.y);
+            y.z = __fsub_rn(__fadd_rn(a2.z, rr.z), b2.z);
+            y.w = __fsub_rn(__fadd_rn(a2.w, rr.w), b2.w);
             if (p.norm == 2) {
-              sp += dp[v].x * dp[v].x + dp[v].y * dp[v].y + dp[v].z * dp[v].z + dp[v].w * dp[v].w;
-              sn += dn[v].x * dn[v].x + dn[v].y * dn[v].y + dn[v].z * dn[v].z + dn[v].w * dn[v].w;
+              sp[u] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+              sn[u] += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
             } else {
-              sp += fabsf(dp[v].x) + fabsf(dp[v].y) + fabsf(dp[v].z) + fabsf(dp[v].w);
-              sn += fabsf(dn[v].x) + fabsf(dn[v].y) + fabsf(dn[v].z) + fabsf(dn[v].w);
+              sp[u] += fabsf(x.x) + fabsf(x.y) + fabsf(x.z) + fabsf(x.w);
+              sn[u] += fabsf(y.x) + fabsf(y.y) + fabsf(y.z) + fabsf(y.w);
             }
           }
         }
-        sp = warp_sum(sp);
-        sn = warp_sum(sn);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        sp[u] = warp_sum(sp[u]);
+        sn[u] = warp_sum(sn[u]);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        float spu = sp[u], snu = sn[u];
         if (p.norm == 2) {
-          sp = sqrtf(sp);
-          sn = sqrtf(sn);
+          spu = sqrtf(spu);
+          snu = sqrtf(snu);
         }
-        const bool active = (sp - sn + p.hp.margin) > 0.f;
-        const float cp = (float)((h == M) - (t == M));
-        const float cn = (float)((h2 == M) - (t2 == M));
-        cnt += (h == M) + (t == M) + (h2 == M) + (t2 == M);
+        const bool active = valid[u] && (spu - snu + p.hp.margin) > 0.f;
+        const float cp = (float)((h[u] == M) - (t[u] == M));
+        const float cn = (float)((h2[u] == M) - (t2[u] == M));
+        if (valid[u]) cnt += (h[u] == M) + (t[u] == M) + (h2[u] == M) + (t2[u] == M);
         if (active) {
           // d||d||_2/dd = d/||d|| (0 at the origin, as torch); d||d||_1/dd = sign(d)
-          const float ip = (p.norm == 2) ? ((sp > 0.f) ? cp / sp : 0.f) : cp;
-          const float in = (p.norm == 2) ? ((sn > 0.f) ? cn / sn : 0.f) : cn;
+          const float ip = (p.norm == 2) ? ((spu > 0.f) ? cp / spu : 0.f) : cp;
+          const float in = (p.norm == 2) ? ((snu > 0.f) ? cn / snu : 0.f) : cn;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
+            const float4 x = dp[u][v], y = dn[u][v];
             if (p.norm == 2) {
-              g[v].x += ip * dp[v].x - in * dn[v].x;
-              g[v].y += ip * dp[v].y - in * dn[v].y;
-              g[v].z += ip * dp[v].z - in * dn[v].z;
-              g[v].w += ip * dp[v].w - in * dn[v].w;
+              g[v].x += ip * x.x - in * y.x;
+              g[v].y += ip * x.y - in * y.y;
+              g[v].z += ip * x.z - in * y.z;
+              g[v].w += ip * x.w - in * y.w;
             } else {
-              g[v].x += ip * sgn(dp[v].x) - in * sgn(dn[v].x);
-              g[v].y += ip * sgn(dp[v].y) - in * sgn(dn[v].y);
-              g[v].z += ip * sgn(dp[v].z) - in * sgn(dn[v].z);
-              g[v].w += ip * sgn(dp[v].w) - in * sgn(dn[v].w);
+              g[v].x += ip * sgn(x.x) - in * sgn(y.x);
+              g[v].y += ip * sgn(x.y) - in * sgn(y.y);
+              g[v].z += ip * sgn(x.z) - in * sgn(y.z);
+              g[v].w += ip * sgn(x.w) - in * sgn(y.w);
             }
           }
         }
       }
-      // all warps have finished READING eM for this step before anyone updates it
-#pragma unroll
-      for (int v = 0; v < VPL; ++v) {
-        const int k = (v * 32 + lane) * 4;
-        if (k < D) *reinterpret_cast<float4*>(gw + warp * D + k) = g[v];
-      }
-      if (lane == 0) s_cnt[warp] = cnt;
-      __syncthreads();
-      ++step;
-      const double bc1 = 1.0 - pow((double)p.hp.beta1, (double)step);
-      const double bc2 = 1.0 - pow((double)p.hp.beta2, (double)step);
-      const float step_size = (float)((double)p.hp.lr / bc1);
-      const float bc2_sqrt = (float)sqrt(bc2);
-      int total_cnt = 0;
-#pragma unroll
-      for (int w = 0; w < TT_WARPS; ++w) total_cnt += s_cnt[w];
-      const float reg = p.hp.reg_weight * (float)total_cnt / (3.f * (float)B * (float)D);
-      const float invB = 1.f / (float)B;
-      for (int k = tid; k < D; k += TT_THREADS) {
-        float gs = 0.f;
-#pragma unroll
-        for (int w = 0; w < TT_WARPS; ++w) gs += gw[w * D + k];
-        const float e = eM[k];
-        const float grad = gs * invB + reg * e;
-        const float m = am[k] + (1.f - p.hp.beta1) * (grad - am[k]);
-        const float v2 = av[k] * p.hp.beta2 + (1.f - p.hp.beta2) * grad * grad;
-        am[k] = m;
-        av[k] = v2;
-        const float denom = sqrtf(v2) / bc2_sqrt + p.hp.eps;
-        eM[k] = e - step_size * (m / denom);
-      }
-      __syncthreads();
     }
+    pf = prefetch(step + 1);  // in flight across the barrier and the optimizer update
+    // all warps have finished READING eM for this step before anyone updates it
+#pragma unroll
+    for (int v = 0; v < VPL; ++v) {
+      const int k = (v * 32 + lane) * 4;
+      if (k < D) *reinterpret_cast<float4*>(gw + warp * D + k) = g[v];
+    }
+    if (lane == 0) s_cnt[warp] = cnt;
+    const float2 bc = p.adam[step];  // (lr / bias_correction1, sqrt(bias_correction2))
+    __syncthreads();
+    int total_cnt = 0;
+#pragma unroll
+    for (int w = 0; w < TT_WARPS; ++w) total_cnt += s_cnt[w];
+    const float reg = p.hp.reg_weight * (float)total_cnt / (3.f * (float)B * (float)D);
+    const float invB = 1.f / (float)B;
+    for (int k = tid; k < D; k += TT_THREADS) {
+      float gs = 0.f;
+#pragma unroll
+      for (int w = 0; w < TT_WARPS; ++w) gs += gw[w * D + k];
+      const float e = eM[k];
+      const float grad = gs * invB + reg * e;
+      const float m = am[k] + (1.f - p.hp.beta1) * (grad - am[k]);
+      const float v2 = av[k] * p.hp.beta2 + (1.f - p.hp.beta2) * grad * grad;
+      am[k] = m;
+      av[k] = v2;
+      const float denom = sqrtf(v2) / bc.y + p.hp.eps;
+      eM[k] = e - bc.x * (m / denom);
+    }
+    __syncthreads();
   }
   for (int k = tid; k < D; k += TT_THREADS) p.out[(size_t)c * D + k] = eM[k];
+}
+
+template <bool CP>
+int launch_train(kp_ctx* ctx, const TrainK& p, int vpl, size_t smem, cudaStream_t st) {
+  if (vpl <= 1) {
+    transe_train_kernel<1, 2, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+  } else if (vpl <= 2) {
+    transe_train_kernel<2, 1, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+  } else if (vpl <= 4) {
+    transe_train_kernel<4, 1, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+  } else if (vpl <= 8) {
+    transe_train_kernel<8, 1, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+  } else {
+    KP_FAIL(ctx, KP_EUNSUPPORTED, "TransE post-training supports dim <= 1024 (got %d)", ctx->D);
+  }
+  return KP_OK;
 }
 
 }  // namespace
 
 int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st) {
-  if (!b->pos || !b->neg) KP_FAIL(ctx, KP_EINVAL, "TransE post-training needs pos and neg rows");
+  if (b->pos_idx) {
+    if (!b->neg_code || !b->facts || !b->fact_off) KP_FAIL(ctx, KP_EINVAL, "compact TransE tables need pos_idx, neg_code, facts and fact_off");
+  } else if (!b->pos || !b->neg) {
+    KP_FAIL(ctx, KP_EINVAL, "TransE post-training needs pos and neg rows (or the compact tables)");
+  }
   TrainK p;
   p.N = (int)ctx->N;
   p.D = ctx->D;
@@ -189,23 +293,30 @@ int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cud
   p.rows_per_epoch = b->rows_per_epoch;
   p.pos = b->pos;
   p.neg = b->neg;
+  p.fact_off = b->fact_off;
+  p.facts = b->facts;
+  p.pos_idx = b->pos_idx;
+  p.neg_code = b->neg_code;
   p.init = b->init_rows;
   p.out = b->out_rows;
   p.hp = *hp;
   const size_t smem = (size_t)(3 + TT_WARPS) * ctx->D * sizeof(float);
   const int vpl = (ctx->D + 127) / 128;
-  KpTimer timer(ctx, kp_ctx::T_TRANSE_TRAIN, st);
-  if (vpl <= 1) {
-    transe_train_kernel<1><<<p.C, TT_THREADS, smem, st>>>(p);
-  } else if (vpl <= 2) {
-    transe_train_kernel<2><<<p.C, TT_THREADS, smem, st>>>(p);
-  } else if (vpl <= 4) {
-    transe_train_kernel<4><<<p.C, TT_THREADS, smem, st>>>(p);
-  } else if (vpl <= 8) {
-    transe_train_kernel<8><<<p.C, TT_THREADS, smem, st>>>(p);
-  } else {
-    KP_FAIL(ctx, KP_EUNSUPPORTED, "TransE post-training supports dim <= 1024 (got %d)", ctx->D);
+  if (hp->batch_size <= 0 || hp->epochs < 0) KP_FAIL(ctx, KP_EINVAL, "TransE post-training needs batch_size > 0");
+  const long long max_steps = (long long)hp->epochs * ((b->max_rows_per_epoch + hp->batch_size - 1) / hp->batch_size);
+  if (p.C <= 0 || max_steps <= 0) {  // nothing to train: the rows stay as initialised
+    if (p.C > 0) KP_CUDA(ctx, cudaMemcpyAsync(b->out_rows, b->init_rows, (size_t)p.C * ctx->D * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    return KP_OK;
   }
+  int rc;
+  if ((rc = kp_ws_reserve(ctx, WsCursor::need((size_t)max_steps, sizeof(float2)), 1)) != KP_OK) return rc;
+  float2* tab = reinterpret_cast<float2*>(ctx->ws_arena[1]);
+  p.adam = tab;
+  KpTimer timer(ctx, kp_ctx::T_TRANSE_TRAIN, st);
+  adam_table_kernel<<<(unsigned)((max_steps + 255) / 256), 256, 0, st>>>((int)max_steps, hp->lr, hp->beta1, hp->beta2, tab);
+  KP_LAUNCHED(ctx, 1);
+  const bool compact = b->pos_idx != nullptr;
+  if ((rc = compact ? launch_train<true>(ctx, p, vpl, smem, st) : launch_train<false>(ctx, p, vpl, smem, st)) != KP_OK) return rc;
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
 }

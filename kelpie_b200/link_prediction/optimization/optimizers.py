@@ -63,7 +63,7 @@ class _KelpieOptimizer(Optimizer):
         ds = self.model.dataset  # KelpieDataset: num_entities = N + 1
         batch = plans.Batch(base.name, ds.num_entities - 1, ds.num_relations, self.hp)
         batch.add(np.array(training_triples).reshape(-1, 3), self.model.kelpie_entity_emb.detach().cpu().numpy())
-        rows = ctx.post_train(runtime.make_hp(base.name, self.hp), **batch.arrays())
+        rows = ctx.post_train(runtime.make_hp(base.name, self.hp), **batch.arrays(compact=True))
         with torch.no_grad():
             self.model.kelpie_entity_emb = rows[:1].clone()
         self.model.update_embeddings()

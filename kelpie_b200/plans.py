@@ -21,8 +21,10 @@ def _rows_with_inverses(facts, num_relations):
     return np.vstack((f, inv)) if len(f) else np.zeros((0, 3), dtype=np.int64)
 
 
-def draw_transe(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
-    """pairwise_ranking_optimizer.py:165-195.  Returns (rows_per_epoch, pos [E*n,3], neg [E*n,3]).
+def draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
+    """pairwise_ranking_optimizer.py:165-195 as COMPACT index tables (kelpie_b200.h, kp_pt_batch.pos_idx / neg_code):
+    returns (rows_per_epoch n, rows [n,3] int32 = triples + inverses, pos_idx [E*n] = which row is the positive,
+    neg_code [E*n] int32 = corrupting entity | head-corrupted << 31).
 
     Reference order (default): per epoch np.random.shuffle(rows) (cumulative: an index vector is shuffled, which
     draws the same numbers and applies the same permutation as shuffling the rows), torch.randint(N+1) then
@@ -33,7 +35,7 @@ def draw_transe(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
     rows = _rows_with_inverses(facts, num_relations)
     n, E, ratio = len(rows), int(hp["epochs"]), int(hp["negative_triples_ratio"])
     if n == 0:
-        return 0, np.zeros((0, 3), np.int32), np.zeros((0, 3), np.int32)
+        return 0, np.zeros((0, 3), np.int32), np.zeros(0, np.int64), np.zeros(0, np.int32)
     take = np.arange(n) // ratio  # first n rows of np.repeat(rows, ratio)
     if fast_rng is not None:
         perm = np.argsort(fast_rng.random((E, n)), axis=1)
@@ -50,12 +52,28 @@ def draw_transe(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
             torch.randint(n_ent_with_mimic, (ratio * n,), out=rnd_t[e])
             torch.randint(2, (ratio * n,), out=coin_t[e])
         rnd, coin = rnd_t.numpy()[:, :n], coin_t.numpy()[:, :n]
-    pos = rows[perm[:, take]].astype(np.int32)  # [E, n, 3]
+    code = (rnd.astype(np.int64) | ((coin == 1).astype(np.int64) << 31)).astype(np.uint32).view(np.int32)
+    return n, rows.astype(np.int32), perm[:, take].reshape(-1), code.reshape(-1)
+
+
+def expand_transe(rows, pos_idx, neg_code):
+    """Compact tables -> the full (pos, neg) [.,3] int32 row tables the reference's step_on_batch sees."""
+    pos = rows[pos_idx].astype(np.int32).reshape(-1, 3)
     neg = pos.copy()
-    head = coin == 1
-    neg[..., 0] = np.where(head, rnd, pos[..., 0])
-    neg[..., 2] = np.where(head, pos[..., 2], rnd)
-    return n, pos.reshape(-1, 3), neg.reshape(-1, 3)
+    code = np.asarray(neg_code).view(np.uint32)
+    head, rnd = (code >> 31) == 1, (code & 0x7FFFFFFF).astype(np.int32)
+    neg[:, 0] = np.where(head, rnd, pos[:, 0])
+    neg[:, 2] = np.where(head, pos[:, 2], rnd)
+    return pos, neg
+
+
+def draw_transe(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
+    """As draw_transe_compact, expanded: returns (rows_per_epoch, pos [E*n,3], neg [E*n,3])."""
+    n, rows, pos_idx, code = draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng)
+    if n == 0:
+        return 0, np.zeros((0, 3), np.int32), np.zeros((0, 3), np.int32)
+    pos, neg = expand_transe(rows, pos_idx, code)
+    return n, pos, neg
 
 
 def draw_transe_full_epoch(rows, num_entities, ratio):
@@ -134,6 +152,7 @@ class Batch:
         self.fast_rng = fast_rng  # None: the reference's generators in the reference's order
         self.init_rows, self.rows_per_epoch = [], []
         self.pos, self.neg, self.pos_lens, self.pos_ids = [], [], [], []
+        self.facts = []  # TransE: each job's distinct rows (triples + inverses)
         self.statics = []
 
     def __len__(self):
@@ -141,10 +160,11 @@ class Batch:
 
     def add(self, facts, init_row):
         """Draw (in reference order) and append one job; returns its index in the batch."""
-        if self.kind == "TransE":
-            n, pos, neg = draw_transe(facts, self.R, self.N + 1, self.hp, self.fast_rng)
-            self.pos.append(pos)
-            self.neg.append(neg)
+        if self.kind == "TransE":  # kept compact; arrays() expands on request
+            n, rows, pos_idx, code = draw_transe_compact(facts, self.R, self.N + 1, self.hp, self.fast_rng)
+            self.facts.append(rows)
+            self.pos.append(pos_idx)
+            self.neg.append(code)
             static = False
         elif self.kind == "ComplEx":
             n, pos, static = draw_complex(facts, self.R, self.hp, self.fast_rng)
@@ -160,7 +180,11 @@ class Batch:
         self.init_rows.append(np.asarray(init_row, dtype=np.float32).reshape(-1))
         return len(self.init_rows) - 1
 
-    def arrays(self):
+    def arrays(self, compact=False):
+        """Flat arrays of kp_pt_batch (keyword arguments of runtime.Context.post_train).  compact (TransE only): the
+        6-bytes-per-row index tables (fact_off / facts / pos_idx / neg_code) instead of pos / neg."""
+        if self.kind == "TransE":
+            return self._arrays_transe(compact and all(len(f) < 65536 for f in self.facts))
         static = all(self.statics)
         if not static:  # mixed batch: unroll the single-epoch jobs so every job is epoch-major
             E = int(self.hp["epochs"])
@@ -176,12 +200,37 @@ class Batch:
             pos=_concat(self.pos, np.int32) if sum(sizes) else np.zeros((1, 3), np.int32),
             static_epochs=static,
         )
-        if self.kind == "TransE":
-            out["neg"] = _concat(self.neg, np.int32) if sum(sizes) else np.zeros((1, 3), np.int32)
         if self.kind == "ConvE":
             lens = np.concatenate(self.pos_lens) if self.pos_lens else np.zeros(0, np.int64)
             off = np.zeros(len(lens) + 1, dtype=np.int64)
             off[1:] = np.cumsum(lens)
             out["pos_off"] = off
             out["pos_ids"] = np.concatenate(self.pos_ids) if len(lens) else np.zeros(1, np.int32)
+        return out
+
+    def _arrays_transe(self, compact):
+        sizes = [len(p) for p in self.pos]
+        row_off = np.zeros(len(sizes) + 1, dtype=np.int64)
+        row_off[1:] = np.cumsum(sizes)
+        out = dict(
+            init_rows=np.stack(self.init_rows).astype(np.float32),
+            row_off=row_off,
+            rows_per_epoch=np.array(self.rows_per_epoch, dtype=np.int32),
+            static_epochs=False,
+        )
+        total = int(row_off[-1])
+        if compact:
+            fact_off = np.zeros(len(sizes) + 1, dtype=np.int64)
+            fact_off[1:] = np.cumsum([len(f) for f in self.facts])
+            out["pos"] = None
+            out["fact_off"] = fact_off
+            out["facts"] = _concat(self.facts, np.int32) if fact_off[-1] else np.zeros((1, 3), np.int32)
+            out["pos_idx"] = _concat(self.pos, np.uint16) if total else np.zeros(1, np.uint16)
+            out["neg_code"] = _concat(self.neg, np.int32) if total else np.zeros(1, np.int32)
+        elif total:
+            full = [expand_transe(f, p, c) for f, p, c in zip(self.facts, self.pos, self.neg) if len(p)]
+            out["pos"] = _concat([x[0] for x in full], np.int32)
+            out["neg"] = _concat([x[1] for x in full], np.int32)
+        else:
+            out["pos"] = out["neg"] = np.zeros((1, 3), np.int32)
         return out

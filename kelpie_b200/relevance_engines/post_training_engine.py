@@ -111,7 +111,7 @@ class PostTrainingEngine(RelevanceEngine):
             if snapshots is not None:  # generator state after this candidate's draws (builder early stop)
                 snapshots.append(self._rng_snapshot())
 
-        arrs = batch.arrays()
+        arrs = batch.arrays(compact=True)  # TransE: 6-byte index rows over PCIe
         hp = runtime.make_hp(kind, self.hp)
         # ConvE dropout masks are counter-based (kp_dropout.cuh); the seed advances per batch and
         # does not touch the host generators (the reference draws its masks on the CUDA generator)

@@ -53,6 +53,7 @@ class PTBatch(Structure):
         ("row_off", c_void_p), ("rows_per_epoch", c_void_p), ("pos", c_void_p), ("neg", c_void_p),
         ("pos_off", c_void_p), ("pos_ids", c_void_p), ("init_rows", c_void_p), ("out_rows", c_void_p),
         ("dropout_seed", c_uint64),
+        ("fact_off", c_void_p), ("facts", c_void_p), ("pos_idx", c_void_p), ("neg_code", c_void_p),  # TransE compact tables
     ]
 
 
@@ -307,9 +308,11 @@ class Context:
                                                self._stream()), "kp_debug_contract")
         return m, l, O
 
-    def post_train(self, hp, init_rows, row_off, rows_per_epoch, pos, neg=None, pos_off=None, pos_ids=None,
-                   static_epochs=False, dropout_seed=0, max_rows_per_epoch=None, total_rows=None):
-        """Run one batch of C mimic post-trainings; returns the [C, D] post-trained rows (device)."""
+    def post_train(self, hp, init_rows, row_off, rows_per_epoch, pos=None, neg=None, pos_off=None, pos_ids=None,
+                   static_epochs=False, dropout_seed=0, max_rows_per_epoch=None, total_rows=None,
+                   fact_off=None, facts=None, pos_idx=None, neg_code=None):
+        """Run one batch of C mimic post-trainings; returns the [C, D] post-trained rows (device).
+        TransE: either pos / neg or the compact tables fact_off / facts / pos_idx (uint16) / neg_code (kelpie_b200.h)."""
         init = self.dev(init_rows, torch.float32).view(-1, self.D)
         C = init.shape[0]
         out = torch.empty_like(init)
@@ -331,7 +334,8 @@ class Context:
         b = PTBatch(C, 1 if static_epochs else 0, int(max_rows_per_epoch), 0, int(total_rows),
                     d(row_off, torch.int64), d(rows_per_epoch, torch.int32),
                     d(pos, torch.int32), d(neg, torch.int32), d(pos_off, torch.int64), d(pos_ids, torch.int32),
-                    _ptr(init), _ptr(out), int(dropout_seed))
+                    _ptr(init), _ptr(out), int(dropout_seed),
+                    d(fact_off, torch.int64), d(facts, torch.int32), d(pos_idx, torch.uint16), d(neg_code, torch.int32))
         self._check(self.lib.kp_post_train_batch(self.handle, ctypes.byref(b), ctypes.byref(hp), self._stream()),
                     "kp_post_train_batch")
         self._keep = keep  # inputs must outlive the asynchronous kernels

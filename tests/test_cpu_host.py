@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(runtime.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.kp_abi_version() == 1
+    assert lib.kp_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -46,7 +46,7 @@ def test_no_cpu_fallback():
 def test_struct_layouts_match_header():
     from kelpie_b200 import runtime
     assert ctypes.sizeof(runtime.HP) == 40
-    assert ctypes.sizeof(runtime.PTBatch) == 96
+    assert ctypes.sizeof(runtime.PTBatch) == 96 + 4 * 8  # ABI 2: the compact TransE tables
     assert ctypes.sizeof(runtime.ConvEWeights) == 7 * 8 + 5 * 4 + 4
 
 
@@ -72,6 +72,11 @@ def test_batch_plans_match_oracle_draws(kind):
         neg = np.concatenate([s["neg"] for s in log])
         np.testing.assert_array_equal(a["pos"], pos)
         np.testing.assert_array_equal(a["neg"], neg)
+        c = b.arrays(compact=True)  # the 6-byte index rows describe the same tables
+        assert c["pos"] is None and c["pos_idx"].dtype == np.uint16 and c["neg_code"].dtype == np.int32
+        cp, cn = plans.expand_transe(c["facts"][c["fact_off"][0]:c["fact_off"][1]], c["pos_idx"], c["neg_code"])
+        np.testing.assert_array_equal(cp, pos)
+        np.testing.assert_array_equal(cn, neg)
     elif kind == "ComplEx":
         assert a["static_epochs"]
         got = sorted(map(tuple, a["pos"]))

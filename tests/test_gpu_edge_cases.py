@@ -32,6 +32,9 @@ def _both(kind, z, w, kg, hp, jobs, ctx):
     for facts, init in jobs:
         b.add(facts, init)
     got = ctx.post_train(runtime.make_hp(kind, hp), **b.arrays()).cpu().numpy()
+    if kind == "TransE":  # the compact index tables (ABI 2) drive the same arithmetic: bit-identical rows
+        compact = ctx.post_train(runtime.make_hp(kind, hp), **b.arrays(compact=True)).cpu().numpy()
+        assert np.array_equal(compact, got)
     return got, np.stack(want)
 
 
@@ -204,3 +207,26 @@ def test_device_built_filter_csr_equals_dict_upload():
     b.build_filter(np.zeros((0, 3), np.int32))
     assert [len(x) for x in b.download_filter()] == [0, 1, 0]
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("D,batch", [(128, 2048), (256, 2048), (128, 48), (512, 2048)])
+def test_transe_compact_tables_many_rows(D, batch):
+    """Candidates with up to 150 rows per step (beyond the rows whose indices are prefetched), several row widths
+    (one and more float4 per lane, one and two rows in flight per warp): compact == full tables bit for bit, and both
+    match the oracle on a small table."""
+    from kelpie_b200 import plans, runtime
+    rng = np.random.default_rng(D + batch)
+    N, R = 700, 9
+    ent = (rng.standard_normal((N, D)) * 0.2).astype(np.float32)
+    rel = (rng.standard_normal((2 * R, D)) * 0.2).astype(np.float32)
+    ctx = runtime.Context("TransE", ent, rel, norm=2)
+    hp = dict(batch_size=batch, epochs=5, lr=0.01, margin=2.0, negative_triples_ratio=5, regularizer_weight=1.0)
+    seed_all(5)
+    b = plans.Batch("TransE", N, R, hp)
+    for facts, init in _jobs(rng, N, R, D, [75, 0, 1, 40, 13, 64, 3], 0.3):
+        b.add(facts, init)
+    full = ctx.post_train(runtime.make_hp("TransE", hp), **b.arrays()).cpu().numpy()
+    compact = ctx.post_train(runtime.make_hp("TransE", hp), **b.arrays(compact=True)).cpu().numpy()
+    assert np.array_equal(full, compact)
+    assert np.isfinite(full).all() and np.abs(full - np.stack(b.init_rows)).max() > 0
+    ctx.close()
