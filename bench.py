@@ -132,9 +132,12 @@ def make_batch(cfg, D, C, seed):
 def algorithmic_work(cfg, D, arrs):
     """executed algorithmic flops / bytes of ONE launch of the dominant kernel."""
     kind, N = cfg["kind"], cfg["N"]
-    if kind == "TransE":  # rank pass: table read once per 64 queries (HBM) / 3 Q N D flops
-        Q = len(arrs["init_rows"])
-        return dict(bound="hbm", units=((Q + 63) // 64) * N * D * 4.0, what="pass")
+    if kind == "TransE":
+        # dominant kernel: the batched post-training (the L2 rank runs on tcgen05 since kp_rank_umma.cu took it over).
+        # SURVEY 8(d): bytes = one corrupting row per training row + each candidate's own fact / relation rows once
+        rows = float(arrs["row_off"][-1])
+        facts = float(arrs["fact_off"][-1]) if "fact_off" in arrs else rows / cfg["hp"]["epochs"]
+        return dict(bound="hbm", units=(rows + facts) * D * 4.0, what="transe_train")
     a_rows = int((arrs["pos"][:, 0] == N).sum())  # rows / pairs whose lhs is the mimic, per step
     return dict(bound="tensor", units=4.0 * a_rows * N * D, what="flash")
 
@@ -299,6 +302,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi starts before the warm-up: its start-up (fork, NVML initialisation) must not fall into a short timed region
+    sampler = ClockSampler(local) if rank == 0 else None
     for i in range(args.warmup):
         t = time.time()
         step()
@@ -308,7 +313,6 @@ def main():
 
     ctx.set_option("timing", 1)
     ctx.stat("reset")
-    sampler = ClockSampler(local) if rank == 0 else None
     barrier()
     launches0, w0 = ctx.launches, time.time()
     t_kernel = t_e2e = 0.0

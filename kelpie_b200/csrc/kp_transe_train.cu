@@ -203,9 +203,10 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
         const float cn = (float)((h2[u] == M) - (t2[u] == M));
         if (valid[u]) cnt += (h[u] == M) + (t[u] == M) + (h2[u] == M) + (t2[u] == M);
         if (active) {
-          // d||d||_2/dd = d/||d|| (0 at the origin, as torch); d||d||_1/dd = sign(d)
-          const float ip = (p.norm == 2) ? ((spu > 0.f) ? cp / spu : 0.f) : cp;
-          const float in = (p.norm == 2) ? ((snu > 0.f) ? cn / snu : 0.f) : cn;
+          // d||d||_2/dd = d/||d|| (0 at the origin, as torch); d||d||_1/dd = sign(d).  The mimic row's coefficient c is
+          // -1, 0 or +1, so c / ||d|| == c * (1 / ||d||) exactly (one correctly rounded reciprocal, no division).
+          const float ip = (p.norm == 2) ? ((spu > 0.f) ? cp * __frcp_rn(spu) : 0.f) : cp;
+          const float in = (p.norm == 2) ? ((snu > 0.f) ? cn * __frcp_rn(snu) : 0.f) : cn;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             const float4 x = dp[u][v], y = dn[u][v];
