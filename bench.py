@@ -211,7 +211,10 @@ def run_reference(cfg, args, D, rank):
         "impl": "reference", "metric": "candidate explanations evaluated/sec (post-train + filtered rank)",
         "value": 1.0 / per, "unit": "candidates/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": per * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": {"workload": args.workload, "candidates_per_step": 1},
+        "data": "synthetic",
+        "config": {"workload": args.workload, "model": kind, "entities": N, "row_floats": D, "relations": R,
+                   "facts_per_candidate": list(cfg["T"]), "epochs": cfg["hp"]["epochs"],
+                   "candidates_per_step": 1, "sample": "each step is ONE candidate of the workload's batch (bounded sample)"},
         "cpu_baseline": {"value": 1.0 / per, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port", "sample": sample},
         "e2e": {"value": 1.0 / per, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
