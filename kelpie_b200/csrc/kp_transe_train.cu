@@ -57,7 +57,7 @@ __global__ void adam_table_kernel(int steps, float lr, float beta1, float beta2,
 
 // VPL: float4 vectors per lane (D <= 128 * VPL).  U: rows a warp has in flight at once (independent gathers).
 // CP: compact index tables (kp_pt_batch.pos_idx / neg_code / facts) instead of pos / neg.
-template <int VPL, int U, bool CP>
+template <int VPL, int U, bool CP, bool L2N>  // L2N: Euclidean norm (every shipped config), else L1
 __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p) {
   extern __shared__ float sm[];
   const int D = p.D;
@@ -88,27 +88,25 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
   // (full tables: pos h, r, t, neg h, r, t; compact: the positive fact's h, r, t and the corruption code).
   constexpr int LPS = CP ? 4 : 6;
   constexpr int PF = 32 / LPS;
-  auto step_base = [&](long long s, int& b0) -> int64_t {
-    const int ep = (int)(s / spe);
-    b0 = (int)(s % spe) * bs;
-    return base0 + (p.static_epochs ? 0 : (int64_t)ep * n) + b0;
-  };
-  auto prefetch = [&](long long s) -> int {
-    if (s >= n_steps || lane >= LPS * PF) return 0;
-    int b0;
-    const int64_t rb = step_base(s, b0);
+  // (epoch, first row) of a step advance incrementally: no 64-bit division per step
+  auto row_base = [&](int ep, int b0) -> int64_t { return base0 + (p.static_epochs ? 0 : (int64_t)ep * n) + b0; };
+  auto prefetch = [&](int ep, int b0) -> int {
+    if (ep >= p.hp.epochs || lane >= LPS * PF) return 0;
+    const int64_t rb = row_base(ep, b0);
     const int B = min(bs, n - b0);
     const int i = warp + TT_WARPS * (lane / LPS), k = lane % LPS;
     if (i >= B) return 0;
     if (CP) return (k == 3) ? p.neg_code[rb + i] : facts[(int)p.pos_idx[rb + i] * 3 + k];
     return (k < 3 ? p.pos : p.neg)[(rb + i) * 3 + (k % 3)];
   };
-  int pf = prefetch(0);
+  int ep = 0, b0 = 0;
+  int pf = (n_steps > 0) ? prefetch(0, 0) : 0;
 
   for (long long step = 0; step < n_steps; ++step) {
-    int b0;
-    const int64_t rb = step_base(step, b0);
+    const int64_t rb = row_base(ep, b0);
     const int B = min(bs, n - b0);
+    int ep1 = ep, b1 = b0 + bs;  // the next step
+    if (b1 >= n) ep1 = ep + 1, b1 = 0;
     float4 g[VPL];
 #pragma unroll
     for (int v = 0; v < VPL; ++v) g[v] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -176,7 +174,7 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
             y.y = __fsub_rn(__fadd_rn(a2.y, rr.y), b2.y);
             y.z = __fsub_rn(__fadd_rn(a2.z, rr.z), b2.z);
             y.w = __fsub_rn(__fadd_rn(a2.w, rr.w), b2.w);
-            if (p.norm == 2) {
+            if (L2N) {
               sp[u] += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
               sn[u] += y.x * y.x + y.y * y.y + y.z * y.z + y.w * y.w;
             } else {
@@ -194,7 +192,7 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         float spu = sp[u], snu = sn[u];
-        if (p.norm == 2) {
+        if (L2N) {
           spu = sqrtf(spu);
           snu = sqrtf(snu);
         }
@@ -205,12 +203,12 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
         if (active) {
           // d||d||_2/dd = d/||d|| (0 at the origin, as torch); d||d||_1/dd = sign(d).  The mimic row's coefficient c is
           // -1, 0 or +1, so c / ||d|| == c * (1 / ||d||) exactly (one correctly rounded reciprocal, no division).
-          const float ip = (p.norm == 2) ? ((spu > 0.f) ? cp * __frcp_rn(spu) : 0.f) : cp;
-          const float in = (p.norm == 2) ? ((snu > 0.f) ? cn * __frcp_rn(snu) : 0.f) : cn;
+          const float ip = L2N ? ((spu > 0.f) ? cp * __frcp_rn(spu) : 0.f) : cp;
+          const float in = L2N ? ((snu > 0.f) ? cn * __frcp_rn(snu) : 0.f) : cn;
 #pragma unroll
           for (int v = 0; v < VPL; ++v) {
             const float4 x = dp[u][v], y = dn[u][v];
-            if (p.norm == 2) {
+            if (L2N) {
               g[v].x += ip * x.x - in * y.x;
               g[v].y += ip * x.y - in * y.y;
               g[v].z += ip * x.z - in * y.z;
@@ -225,7 +223,8 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
         }
       }
     }
-    pf = prefetch(step + 1);  // in flight across the barrier and the optimizer update
+    pf = prefetch(ep1, b1);  // in flight across the barrier and the optimizer update
+    ep = ep1, b0 = b1;
     // all warps have finished READING eM for this step before anyone updates it
 #pragma unroll
     for (int v = 0; v < VPL; ++v) {
@@ -258,16 +257,16 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
   for (int k = tid; k < D; k += TT_THREADS) p.out[(size_t)c * D + k] = eM[k];
 }
 
-template <bool CP>
+template <bool CP, bool L2N>
 int launch_train(kp_ctx* ctx, const TrainK& p, int vpl, size_t smem, cudaStream_t st) {
   if (vpl <= 1) {
-    transe_train_kernel<1, 2, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+    transe_train_kernel<1, 2, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 2) {
-    transe_train_kernel<2, 1, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+    transe_train_kernel<2, 1, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 4) {
-    transe_train_kernel<4, 1, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+    transe_train_kernel<4, 1, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 8) {
-    transe_train_kernel<8, 1, CP><<<p.C, TT_THREADS, smem, st>>>(p);
+    transe_train_kernel<8, 1, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
   } else {
     KP_FAIL(ctx, KP_EUNSUPPORTED, "TransE post-training supports dim <= 1024 (got %d)", ctx->D);
   }
@@ -317,7 +316,10 @@ int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cud
   adam_table_kernel<<<(unsigned)((max_steps + 255) / 256), 256, 0, st>>>((int)max_steps, hp->lr, hp->beta1, hp->beta2, tab);
   KP_LAUNCHED(ctx, 1);
   const bool compact = b->pos_idx != nullptr;
-  if ((rc = compact ? launch_train<true>(ctx, p, vpl, smem, st) : launch_train<false>(ctx, p, vpl, smem, st)) != KP_OK) return rc;
+  const bool l2n = ctx->norm == 2;
+  rc = compact ? (l2n ? launch_train<true, true>(ctx, p, vpl, smem, st) : launch_train<true, false>(ctx, p, vpl, smem, st))
+               : (l2n ? launch_train<false, true>(ctx, p, vpl, smem, st) : launch_train<false, false>(ctx, p, vpl, smem, st));
+  if (rc != KP_OK) return rc;
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
 }
