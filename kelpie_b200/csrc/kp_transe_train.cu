@@ -57,7 +57,7 @@ __global__ void adam_table_kernel(int steps, float lr, float beta1, float beta2,
 
 // VPL: float4 vectors per lane (D <= 128 * VPL).  U: rows a warp has in flight at once (independent gathers).
 // CP: compact index tables (kp_pt_batch.pos_idx / neg_code / facts) instead of pos / neg.
-template <int VPL, int U, bool CP, bool L2N>  // L2N: Euclidean norm (every shipped config), else L1
+template <int VPL, int U, bool CP, bool L2N, bool EX>  // L2N: Euclidean norm (every shipped config), else L1; EX: D == 128 * VPL
 __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p) {
   extern __shared__ float sm[];
   const int D = p.D;
@@ -80,6 +80,15 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
   __syncthreads();
 
   const int M = p.N;
+  // rows are addressed in float4 units with 32-bit offsets: one IMAD per gathered vector instead of 64-bit pointer
+  // arithmetic and generic (shared-or-global) loads
+  const float4* __restrict__ ent4 = reinterpret_cast<const float4*>(p.ent);
+  const unsigned d4 = (unsigned)D >> 2;
+  const float4* __restrict__ rel4 = reinterpret_cast<const float4*>(p.rel);
+  auto ldrow = [&](int e, int k) -> float4 {
+    if (e == M) return *reinterpret_cast<const float4*>(eM + k);  // warp-uniform
+    return ent4[(unsigned)e * d4 + (unsigned)(k >> 2)];
+  };
   const int bs = p.hp.batch_size;
   const int spe = (n + bs - 1) / bs;  // steps per epoch
   const long long n_steps = (long long)p.hp.epochs * spe;
@@ -151,19 +160,14 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
       float sp[U], sn[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        const float* ph = (h[u] == M) ? eM : p.ent + (size_t)h[u] * D;
-        const float* pt = (t[u] == M) ? eM : p.ent + (size_t)t[u] * D;
-        const float* ph2 = (h2[u] == M) ? eM : p.ent + (size_t)h2[u] * D;
-        const float* pt2 = (t2[u] == M) ? eM : p.ent + (size_t)t2[u] * D;
-        const float* prl = p.rel + (size_t)r[u] * D;
         sp[u] = sn[u] = 0.f;
 #pragma unroll
         for (int v = 0; v < VPL; ++v) {
           const int k = (v * 32 + lane) * 4;
           dp[u][v] = dn[u][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (k < D) {
-            const float4 a = ld4(ph + k), rr = ld4(prl + k), b = ld4(pt + k);
-            const float4 a2 = ld4(ph2 + k), b2 = ld4(pt2 + k);
+          if (EX || k < D) {
+            const float4 a = ldrow(h[u], k), rr = rel4[(unsigned)r[u] * d4 + (unsigned)(k >> 2)], b = ldrow(t[u], k);
+            const float4 a2 = ldrow(h2[u], k), b2 = ldrow(t2[u], k);
             float4& x = dp[u][v];
             float4& y = dn[u][v];
             x.x = __fsub_rn(__fadd_rn(a.x, rr.x), b.x);
@@ -259,14 +263,19 @@ __global__ void __launch_bounds__(TT_THREADS) transe_train_kernel(const TrainK p
 
 template <bool CP, bool L2N>
 int launch_train(kp_ctx* ctx, const TrainK& p, int vpl, size_t smem, cudaStream_t st) {
+  const bool ex = ctx->D == 128 * vpl;
   if (vpl <= 1) {
-    transe_train_kernel<1, 2, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
+    if (ex) transe_train_kernel<1, 2, CP, L2N, true><<<p.C, TT_THREADS, smem, st>>>(p);
+    else transe_train_kernel<1, 2, CP, L2N, false><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 2) {
-    transe_train_kernel<2, 1, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
+    if (ex) transe_train_kernel<2, 1, CP, L2N, true><<<p.C, TT_THREADS, smem, st>>>(p);
+    else transe_train_kernel<2, 1, CP, L2N, false><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 4) {
-    transe_train_kernel<4, 1, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
+    if (ex) transe_train_kernel<4, 1, CP, L2N, true><<<p.C, TT_THREADS, smem, st>>>(p);
+    else transe_train_kernel<4, 1, CP, L2N, false><<<p.C, TT_THREADS, smem, st>>>(p);
   } else if (vpl <= 8) {
-    transe_train_kernel<8, 1, CP, L2N><<<p.C, TT_THREADS, smem, st>>>(p);
+    if (ex) transe_train_kernel<8, 1, CP, L2N, true><<<p.C, TT_THREADS, smem, st>>>(p);
+    else transe_train_kernel<8, 1, CP, L2N, false><<<p.C, TT_THREADS, smem, st>>>(p);
   } else {
     KP_FAIL(ctx, KP_EUNSUPPORTED, "TransE post-training supports dim <= 1024 (got %d)", ctx->D);
   }
@@ -316,6 +325,9 @@ int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cud
   adam_table_kernel<<<(unsigned)((max_steps + 255) / 256), 256, 0, st>>>((int)max_steps, hp->lr, hp->beta1, hp->beta2, tab);
   KP_LAUNCHED(ctx, 1);
   const bool compact = b->pos_idx != nullptr;
+  if ((unsigned long long)(ctx->N + 1) * (unsigned long long)(ctx->D / 4) >= (1ull << 32) ||
+      (unsigned long long)ctx->R2 * (unsigned long long)(ctx->D / 4) >= (1ull << 32))
+    KP_FAIL(ctx, KP_EUNSUPPORTED, "TransE post-training addresses rows with 32-bit float4 offsets (table too large)");
   const bool l2n = ctx->norm == 2;
   rc = compact ? (l2n ? launch_train<true, true>(ctx, p, vpl, smem, st) : launch_train<true, false>(ctx, p, vpl, smem, st))
                : (l2n ? launch_train<false, true>(ctx, p, vpl, smem, st) : launch_train<false, false>(ctx, p, vpl, smem, st));
