@@ -50,6 +50,7 @@ __global__ void cx_lse(int G, int n_strips, const float* __restrict__ pm, const 
 struct CxUpd {
   int C, N, D, GA, n_strips, optimizer;
   long long step;  // 1-based optimiser step (Adam bias correction)
+  float step_size, bc2_sqrt;  // Adam: lr / (1 - beta1^step), sqrt(1 - beta2^step), evaluated in double on the host like torch
   float lr, beta1, beta2, eps, n3;
   const float* ent;
   const float* rel;
@@ -152,11 +153,6 @@ __global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
   }
   // N3 (regularizers.py:37-46): w/B * sum_rows |f|^3, f = sqrt(re^2 + im^2) of lhs and rhs rows
   const float cntM = (float)(nA + nB + p.nSelf[c]);
-  double bc1 = 1.0, bc2 = 1.0;
-  if (p.optimizer == KP_OPT_ADAM) {
-    bc1 = 1.0 - pow((double)p.beta1, (double)p.step);
-    bc2 = 1.0 - pow((double)p.beta2, (double)p.step);
-  }
   for (int k = tid; k < D; k += UPD_THREADS) {
     float g = grad[k];
     const float e = eM[k];
@@ -176,8 +172,8 @@ __global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
       const float v = p.st2[idx] * p.beta2 + (1.f - p.beta2) * g * g;
       p.st1[idx] = m;
       p.st2[idx] = v;
-      const float denom = sqrtf(v) / (float)sqrt(bc2) + p.eps;
-      out = e - (float)((double)p.lr / bc1) * (m / denom);
+      const float denom = sqrtf(v) / p.bc2_sqrt + p.eps;
+      out = e - p.step_size * (m / denom);
     } else {
       out = e - p.lr * g;
     }
@@ -281,6 +277,8 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       CxUpd u;
       u.C = C; u.N = (int)ctx->N; u.D = D; u.GA = (int)GA; u.n_strips = ns; u.optimizer = hp->optimizer;
       u.step = t + 1;
+      u.step_size = (float)((double)hp->lr / (1.0 - pow((double)hp->beta1, (double)(t + 1))));
+      u.bc2_sqrt = (float)sqrt(1.0 - pow((double)hp->beta2, (double)(t + 1)));
       u.lr = hp->lr; u.beta1 = hp->beta1; u.beta2 = hp->beta2; u.eps = hp->eps; u.n3 = hp->reg_weight;
       u.ent = ctx->ent; u.rel = ctx->rel;
       u.nA = pl.nA; u.nB = pl.nB; u.nSelf = pl.nSelf; u.aoff = pl.aoff; u.boff = pl.boff;

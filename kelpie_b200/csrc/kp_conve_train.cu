@@ -216,6 +216,7 @@ __global__ void __launch_bounds__(CT) cv_backward_generic(const CvBack p) {
 struct CvUpd {
   int C, N, D;
   long long step;
+  float step_size, bc2_sqrt;  // Adam: lr / (1 - beta1^step), sqrt(1 - beta2^step), evaluated in double on the host like torch
   float lr, beta1, beta2, eps, ta, tb;
   const int32_t *nA, *nB;
   const int64_t *aoff, *boff;
@@ -251,8 +252,6 @@ __global__ void __launch_bounds__(CT) cv_update(const CvUpd p) {
     for (int k = tid; k < D; k += CT) grad[k] += coef * x[k];
   }
   __syncthreads();
-  const double bc1 = 1.0 - pow((double)p.beta1, (double)p.step);
-  const double bc2 = 1.0 - pow((double)p.beta2, (double)p.step);
   for (int k = tid; k < D; k += CT) {
     const size_t idx = (size_t)c * D + k;
     const float g = grad[k];
@@ -260,8 +259,8 @@ __global__ void __launch_bounds__(CT) cv_update(const CvUpd p) {
     const float v = p.st2[idx] * p.beta2 + (1.f - p.beta2) * g * g;
     p.st1[idx] = m;
     p.st2[idx] = v;
-    const float denom = sqrtf(v) / (float)sqrt(bc2) + p.eps;
-    p.mim[idx] = eM[k] - (float)((double)p.lr / bc1) * (m / denom);
+    const float denom = sqrtf(v) / p.bc2_sqrt + p.eps;
+    p.mim[idx] = eM[k] - p.step_size * (m / denom);
   }
 }
 
@@ -381,6 +380,8 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
     if (GA + GB > 0) {
       CvUpd u;
       u.C = C; u.N = (int)ctx->N; u.D = D; u.step = t + 1;
+      u.step_size = (float)((double)hp->lr / (1.0 - pow((double)hp->beta1, (double)(t + 1))));
+      u.bc2_sqrt = (float)sqrt(1.0 - pow((double)hp->beta2, (double)(t + 1)));
       u.lr = hp->lr; u.beta1 = hp->beta1; u.beta2 = hp->beta2; u.eps = hp->eps; u.ta = ta; u.tb = tb;
       u.nA = pl.nA; u.nB = pl.nB; u.aoff = pl.aoff; u.boff = pl.boff;
       u.xA = xA; u.glhs = glhs; u.colcoef = colcoef; u.xB = xB; u.mim = mim; u.st1 = st1; u.st2 = st2;
