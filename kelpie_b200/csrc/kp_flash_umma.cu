@@ -461,7 +461,7 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;
-  static bool configured = false;
+  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U_SMEM));
     configured = true;

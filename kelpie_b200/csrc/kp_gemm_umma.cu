@@ -349,7 +349,7 @@ int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, in
   }
   p.C = C;
   p.ldc = ldc;
-  static bool configured = false;
+  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
     KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
@@ -425,7 +425,7 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
   p.C = C;
   p.ldc = ldc;
-  static bool configured = false;
+  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
     configured = true;

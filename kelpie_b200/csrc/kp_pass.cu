@@ -236,7 +236,7 @@ pass_kernel(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CU
 
 template <int OP>
 int launch(kp_ctx* ctx, const CUtensorMap& qmap, const PassK& p, dim3 grid, cudaStream_t st) {
-  static bool configured = false;
+  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(pass_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
     configured = true;

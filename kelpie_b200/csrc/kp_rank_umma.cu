@@ -455,7 +455,7 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   p.pairs = pairs;
   p.n_pairs = n_pairs;
   p.cap_pairs = cap;
-  static bool configured = false;
+  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
     KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));

@@ -230,3 +230,36 @@ def test_transe_compact_tables_many_rows(D, batch):
     assert np.array_equal(full, compact)
     assert np.isfinite(full).all() and np.abs(full - np.stack(b.init_rows)).max() > 0
     ctx.close()
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+@pytest.mark.parametrize("kind", ["TransE", "ComplEx"])
+def test_two_devices_in_one_process(kind):
+    """One context per GPU inside ONE process (a thread per context instead of a process per GPU): the kernels'
+    shared-memory opt-in is a per-device attribute and must be set on every device, not once per process."""
+    from kelpie_b200 import plans, runtime
+    rng = np.random.default_rng(5)
+    N, R, D = 3001, 6, 512 if kind == "ComplEx" else 256
+    ent = (rng.standard_normal((N, D)) * 0.2).astype(np.float32)
+    rel = (rng.standard_normal((2 * R, D)) * 0.2).astype(np.float32)
+    hp = (dict(optimizer_name="Adagrad", batch_size=512, epochs=3, lr=0.043, decay1=0.9, decay2=0.999, regularizer_name="N3",
+               regularizer_weight=0) if kind == "ComplEx" else
+          dict(batch_size=2048, epochs=3, lr=0.01, margin=2.0, negative_triples_ratio=5, regularizer_weight=1.0))
+    jobs = _jobs(rng, N, R, D, [5] * 300, 1e-3 if kind == "ComplEx" else 0.3)
+    triples = np.tile(np.array([[N, 1, 7]], dtype=np.int32), (len(jobs), 1))
+    off, ids = np.zeros(len(jobs) + 1, np.int64), np.zeros(1, np.int32)
+    out = []
+    for dev in (1, 0):  # the second device first: a per-process flag would leave it unconfigured
+        seed_all(9)
+        b = plans.Batch(kind, N, R, hp)
+        for facts, init in jobs:
+            b.add(facts, init)
+        with torch.cuda.device(dev):
+            ctx = runtime.Context(kind, ent, rel, norm=2, device=dev)
+            rows = ctx.post_train(runtime.make_hp(kind, hp), **b.arrays(compact=True))
+            mode = runtime.RANK_ENGINE_MIN if kind == "TransE" else runtime.RANK_ENGINE_MAX
+            ts, bs, rk = ctx.filtered_rank(triples, mode, mimic_rows=rows, flt_off=off, flt_ids=ids)
+            out.append((rows.cpu().numpy(), rk.cpu().numpy()))
+            ctx.close()
+    assert np.array_equal(out[0][1], out[1][1])
+    np.testing.assert_allclose(out[0][0], out[1][0], rtol=1e-5, atol=1e-7)
