@@ -21,6 +21,18 @@ def _rows_with_inverses(facts, num_relations):
     return np.vstack((f, inv)) if len(f) else np.zeros((0, 3), dtype=np.int64)
 
 
+def _randint_epochs(E, m, n, high):
+    """`for e in range(E): a = torch.randint(high, (m,)); b = torch.randint(2, (m,))`, the first n of each.  The calls stay
+    separate: torch's bounded integers are not a fixed function of consecutive generator words (checked on torch 2.11:
+    one large draw does not reproduce them), so the reference's numbers need the reference's call sequence."""
+    rnd_t = torch.empty((E, m), dtype=torch.int64)
+    coin_t = torch.empty((E, m), dtype=torch.int64)
+    for e in range(E):
+        torch.randint(high, (m,), out=rnd_t[e])
+        torch.randint(2, (m,), out=coin_t[e])
+    return rnd_t.numpy()[:, :n], coin_t.numpy()[:, :n]
+
+
 def draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng=None):
     """pairwise_ranking_optimizer.py:165-195 as COMPACT index tables (kelpie_b200.h, kp_pt_batch.pos_idx / neg_code):
     returns (rows_per_epoch n, rows [n,3] int32 = triples + inverses, pos_idx [E*n] = which row is the positive,
@@ -43,15 +55,11 @@ def draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng=Non
         coin = fast_rng.integers(0, 2, (E, n))
     else:
         perm = np.empty((E, n), dtype=np.int64)
-        rnd_t = torch.empty((E, ratio * n), dtype=torch.int64)
-        coin_t = torch.empty((E, ratio * n), dtype=torch.int64)
         idx = np.arange(n)
-        for e in range(E):
+        for e in range(E):  # numpy's generator is independent of torch's: all shuffles first, same numbers
             np.random.shuffle(idx)
             perm[e] = idx
-            torch.randint(n_ent_with_mimic, (ratio * n,), out=rnd_t[e])
-            torch.randint(2, (ratio * n,), out=coin_t[e])
-        rnd, coin = rnd_t.numpy()[:, :n], coin_t.numpy()[:, :n]
+        rnd, coin = _randint_epochs(E, ratio * n, n, n_ent_with_mimic)
     code = (rnd.astype(np.int64) | ((coin == 1).astype(np.int64) << 31)).astype(np.uint32).view(np.int32)
     return n, rows.astype(np.int32), perm[:, take].reshape(-1), code.reshape(-1)
 
