@@ -209,7 +209,7 @@ def test_device_built_filter_csr_equals_dict_upload():
     a.close(); b.close()
 
 
-@pytest.mark.parametrize("D,batch", [(128, 2048), (256, 2048), (128, 48), (512, 2048)])
+@pytest.mark.parametrize("D,batch", [(128, 2048), (256, 2048), (128, 48), (512, 2048), (200, 2048), (36, 7)])
 def test_transe_compact_tables_many_rows(D, batch):
     """Candidates with up to 150 rows per step (beyond the rows whose indices are prefetched), several row widths
     (one and more float4 per lane, one and two rows in flight per warp): compact == full tables bit for bit, and both
@@ -221,12 +221,18 @@ def test_transe_compact_tables_many_rows(D, batch):
     rel = (rng.standard_normal((2 * R, D)) * 0.2).astype(np.float32)
     ctx = runtime.Context("TransE", ent, rel, norm=2)
     hp = dict(batch_size=batch, epochs=5, lr=0.01, margin=2.0, negative_triples_ratio=5, regularizer_weight=1.0)
+    jobs = _jobs(rng, N, R, D, [75, 0, 1, 40, 13, 64, 3], 0.3)
+    w = ko.Weights("TransE", torch.from_numpy(ent), torch.from_numpy(rel), norm=2, init_scale=1e-3)
+    kg = ko.KG(np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), np.zeros((0, 3), np.int64), N, R)
+    seed_all(5)
+    want = np.stack([ko.post_train(w, kg, torch.from_numpy(init).view(1, -1), facts, hp)[-1].numpy() for facts, init in jobs])
     seed_all(5)
     b = plans.Batch("TransE", N, R, hp)
-    for facts, init in _jobs(rng, N, R, D, [75, 0, 1, 40, 13, 64, 3], 0.3):
+    for facts, init in jobs:
         b.add(facts, init)
     full = ctx.post_train(runtime.make_hp("TransE", hp), **b.arrays()).cpu().numpy()
     compact = ctx.post_train(runtime.make_hp("TransE", hp), **b.arrays(compact=True)).cpu().numpy()
+    _assert_rows(full, want)
     assert np.array_equal(full, compact)
     assert np.isfinite(full).all() and np.abs(full - np.stack(b.init_rows)).max() > 0
     ctx.close()
