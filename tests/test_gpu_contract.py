@@ -44,7 +44,7 @@ def _check(ctx, q, ent, mode, tol=2e-5):
     assert (np.abs(O - rO).max(axis=1) <= tol * cond.max(axis=1)).all()
 
 
-@pytest.mark.parametrize("D,N,G", [(512, 20011, 300), (400, 9001, 1400), (512, 3001, 260), (256, 9001, 300), (128, 5000, 100)])
+@pytest.mark.parametrize("D,N,G", [(512, 20011, 300), (400, 9001, 1400), (512, 3001, 260), (256, 9001, 300), (128, 5000, 100), (272, 5003, 300), (304, 5003, 520)])
 @pytest.mark.parametrize("mode", [0, 1])
 def test_contract_matches_fp64(D, N, G, mode):
     from kelpie_b200 import runtime
