@@ -391,7 +391,7 @@ def main():
             "clocks": sampler.summary(w0, w1) if sampler else None,
             "relevance_checksum": float(np.nansum(rel_vals)),
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # rank 0 at N = 1 only: the other ranks must not idle behind a CPU run
             line["cpu_baseline"] = cpu_baseline(cfg, D, ent, rel, conve)
         print(json.dumps(line))
     if world > 1:

@@ -274,6 +274,22 @@ int64_t kp_conve_fit_launches(const kp_vfit* fit);
 int kp_dp_relevance(kp_ctx* ctx, int32_t n_jobs, const int32_t* preds, const int32_t* facts, const int32_t* entity,
                     float epsilon, float lambd, int32_t sufficient, float* out, void* stream);
 
+/* Host-side replay of the reference's per-epoch random draws (no device work; kp_host_rng.cu).  Both host generators
+ * the Kelpie optimizers consume are 32-bit Mersenne Twisters -- torch's default CPU generator and numpy's legacy global
+ * RandomState -- and each draw is a fixed function of consecutive output words.  key: the 624 state words, *pos: index of
+ * the next word (624 = regenerate first); both are advanced in place exactly as the reference's calls would.
+ *   kp_mt19937_words: the next `count` tempered words (out == NULL only advances; torch.randperm(n) consumes n - 1).
+ *   kp_replay_transe_corruptions (pairwise_ranking_optimizer.py:171-172,187-195): per epoch torch.randint(high, (drawn,))
+ *     then torch.randint(2, (drawn,)), of which the first `used` are kept:
+ *     neg_code[e * used + i] = corrupting entity | head-corrupted << 31 (the compact table of kp_pt_batch), high <= 2^31;
+ *     element = word % high, which is what torch (2.11) computes for high < 2^28 (two words per element above).
+ *   kp_replay_numpy_shuffles (:167-168): `epochs` cumulative np.random.shuffle calls on one index vector of length n;
+ *     perm[e * n + i] = its content after shuffle e (Fisher-Yates from the back, masked rejection sampling). */
+int kp_mt19937_words(uint32_t* key, int32_t* pos, int64_t count, uint32_t* out);
+int kp_replay_transe_corruptions(uint32_t* key, int32_t* pos, int32_t epochs, int64_t drawn, int64_t used, uint32_t high,
+                                 int32_t* neg_code);
+int kp_replay_numpy_shuffles(uint32_t* key, int32_t* pos, int32_t epochs, int32_t n, int32_t* perm);
+
 /* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
  * n_rows query vectors [n_rows, D] (device) against the resident entity table:
  *   out_m[g] = max_j z_gj (softmax: the reference max used, >= true max - 8),  out_l[g] = sum_j p_gj,

@@ -6,6 +6,7 @@ EXACTLY the order the reference's Kelpie*Optimizer does 
 index tables the CUDA kernels read, so that a batch of jobs drawn one after the other
 reproduces the reference's sequential run.
 """
+import os
 from collections import defaultdict
 
 import numpy as np
@@ -21,10 +22,131 @@ def _rows_with_inverses(facts, num_relations):
     return np.vstack((f, inv)) if len(f) else np.zeros((0, 3), dtype=np.int64)
 
 
+class HostReplay:
+    """Native replay of the reference's per-epoch generator calls (kp_host_rng.cu behind the C ABI).
+
+    torch's default CPU generator and numpy's legacy global RandomState are both 32-bit Mersenne Twisters and
+    `torch.randint(high < 2^32)`, `torch.randperm` and `np.random.shuffle` are fixed functions of consecutive output
+    words, so the 3 * epochs Python calls of one TransE post-training (2 * epochs randint, epochs shuffles) become two
+    native calls that produce the SAME numbers and leave both generators advanced as the reference's calls would (the
+    next `torch.rand` of an init row continues from there).  torch's state travels through `get_rng_state` /
+    `set_rng_state` (seed u64, left i32, seeded i32, next u64, 624 key words stored as u64, then the normal-distribution
+    cache: 5056 bytes); numpy's is walked in place through the bit generator's `ctypes.state_address` (624 key words,
+    then the position).  `available()` checks every replay against torch / numpy themselves once per process, on the
+    live and on a freshly seeded state; where one does not reproduce (another torch or numpy, another generator) the
+    callers keep the per-call path."""
+
+    _N, _SIZE = 624, 5056
+    MAX_HIGH = 1 << 28  # torch 2.11 reduces 64-bit words (two generator words per element) from this range on
+    _ok = None
+    _lib = None
+    _np_addr = None
+
+    @classmethod
+    def lib(cls):
+        if cls._lib is None:
+            from . import runtime
+            cls._lib = runtime.load_library()
+        return cls._lib
+
+    # ---- torch's default CPU generator
+    @classmethod
+    def torch_state(cls):
+        buf = torch.get_rng_state().numpy()
+        if buf.size != cls._SIZE:
+            raise RuntimeError("unknown torch CPU generator state layout")
+        key = buf[24:24 + 8 * cls._N].view(np.uint64).astype(np.uint32)
+        left, nxt = int(buf[8:12].view(np.int32)[0]), int(buf[16:24].view(np.uint64)[0])
+        pos = np.array([cls._N if (left == 1 and nxt == 0) else nxt], dtype=np.int32)  # freshly seeded: regenerate first
+        return buf, key, pos
+
+    @classmethod
+    def torch_commit(cls, buf, key, pos):
+        buf[24:24 + 8 * cls._N].view(np.uint64)[:] = key
+        buf[16:24].view(np.uint64)[0] = int(pos[0])
+        buf[8:12].view(np.int32)[0] = cls._N + 1 - int(pos[0])  # torch keeps left + next == 625
+        buf[12:16].view(np.int32)[0] = 1
+        torch.set_rng_state(torch.from_numpy(buf))
+
+    @classmethod
+    def torch_skip(cls, count):
+        """Advance torch's generator by `count` words (E calls of torch.randperm(n): E * (n - 1))."""
+        buf, key, pos = cls.torch_state()
+        rc = cls.lib().kp_mt19937_words(key.ctypes.data, pos.ctypes.data, int(count), None)
+        assert rc == 0, rc
+        cls.torch_commit(buf, key, pos)
+
+    @classmethod
+    def transe_corruptions(cls, E, drawn, used, high):
+        """neg_code [E * used] int32 of `for e: torch.randint(high, (drawn,)); torch.randint(2, (drawn,))`, first `used`."""
+        code = np.empty(E * used, dtype=np.int32)
+        buf, key, pos = cls.torch_state()
+        rc = cls.lib().kp_replay_transe_corruptions(key.ctypes.data, pos.ctypes.data, E, drawn, used, high, code.ctypes.data)
+        assert rc == 0, rc
+        cls.torch_commit(buf, key, pos)
+        return code
+
+    # ---- numpy's legacy global RandomState
+    @classmethod
+    def numpy_shuffles(cls, E, n):
+        """[E, n] int32: an index vector after each of E cumulative np.random.shuffle calls."""
+        if cls._np_addr is None:
+            bg = np.random.mtrand._rand._bit_generator
+            if type(bg).__name__ != "MT19937":
+                raise RuntimeError("numpy's global generator is not an MT19937")
+            cls._np_bg = bg  # keeps the state alive
+            addr = bg.ctypes.state_address
+            cls._np_addr = int(getattr(addr, "value", addr))
+        perm = np.empty((E, n), dtype=np.int32)
+        rc = cls.lib().kp_replay_numpy_shuffles(cls._np_addr, cls._np_addr + 4 * cls._N, E, n, perm.ctypes.data)
+        assert rc == 0, rc
+        return perm
+
+    @classmethod
+    def available(cls):
+        if cls._ok is None and os.environ.get("KELPIE_HOST_REPLAY") == "0":  # A/B switch: per-call draws
+            cls._ok = False
+        if cls._ok is None:
+            saved_t, saved_n = torch.get_rng_state(), np.random.get_state()
+            try:
+                ok = True
+                for seed in (None, 12345):  # the live states, and freshly seeded ones
+                    if seed is not None:
+                        torch.manual_seed(seed)
+                        np.random.seed(seed)
+                    start_t, start_n = torch.get_rng_state(), np.random.get_state()
+                    code = cls.transe_corruptions(3, 700, 650, 24621)
+                    cls.torch_skip(2 * 9)
+                    tail_t = torch.rand(5)
+                    perm = cls.numpy_shuffles(3, 37)
+                    tail_n = np.random.random(3)
+                    torch.set_rng_state(start_t)
+                    np.random.set_state(start_n)
+                    for e in range(3):
+                        rnd = torch.randint(24621, (700,)).numpy()[:650]
+                        coin = torch.randint(2, (700,)).numpy()[:650]
+                        ref = (rnd | (coin << 31)).astype(np.uint32).view(np.int32)
+                        ok = ok and np.array_equal(code[e * 650:(e + 1) * 650], ref)
+                    torch.randperm(10), torch.randperm(10)
+                    ok = ok and torch.equal(tail_t, torch.rand(5))
+                    idx = np.arange(37)
+                    for e in range(3):
+                        np.random.shuffle(idx)
+                        ok = ok and np.array_equal(perm[e], idx)
+                    ok = ok and np.array_equal(tail_n, np.random.random(3))
+                cls._ok = bool(ok)
+            except Exception:
+                cls._ok = False
+            finally:
+                torch.set_rng_state(saved_t)
+                np.random.set_state(saved_n)
+        return cls._ok
+
+
 def _randint_epochs(E, m, n, high):
-    """`for e in range(E): a = torch.randint(high, (m,)); b = torch.randint(2, (m,))`, the first n of each.  The calls stay
-    separate: torch's bounded integers are not a fixed function of consecutive generator words (checked on torch 2.11:
-    one large draw does not reproduce them), so the reference's numbers need the reference's call sequence."""
+    """`for e in range(E): a = torch.randint(high, (m,)); b = torch.randint(2, (m,))`, the first n of each, call by call
+    (the path kept for a torch whose generator HostReplay does not reproduce; one large draw with a single range
+    cannot reproduce them)."""
     rnd_t = torch.empty((E, m), dtype=torch.int64)
     coin_t = torch.empty((E, m), dtype=torch.int64)
     for e in range(E):
@@ -53,10 +175,15 @@ def draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng=Non
         perm = np.argsort(fast_rng.random((E, n)), axis=1)
         rnd = fast_rng.integers(0, n_ent_with_mimic, (E, n))
         coin = fast_rng.integers(0, 2, (E, n))
+    elif n_ent_with_mimic < HostReplay.MAX_HIGH and HostReplay.available():
+        # numpy's generator is independent of torch's: all shuffles first, same numbers
+        perm = HostReplay.numpy_shuffles(E, n)
+        code = HostReplay.transe_corruptions(E, ratio * n, n, n_ent_with_mimic)
+        return n, rows.astype(np.int32), perm[:, take].reshape(-1), code
     else:
         perm = np.empty((E, n), dtype=np.int64)
         idx = np.arange(n)
-        for e in range(E):  # numpy's generator is independent of torch's: all shuffles first, same numbers
+        for e in range(E):
             np.random.shuffle(idx)
             perm[e] = idx
         rnd, coin = _randint_epochs(E, ratio * n, n, n_ent_with_mimic)
@@ -114,8 +241,12 @@ def draw_complex(facts, num_relations, hp, fast_rng=None):
         # one step per epoch over ALL rows: the permutation cannot change a mean over the
         # batch, so one epoch of rows is reused; the generator is still advanced as the
         # reference's torch.randperm would.
-        for _ in range(E):
-            torch.randperm(n)
+        if HostReplay.available():  # torch.randperm(n) consumes n - 1 words of the generator
+            if n > 1:
+                HostReplay.torch_skip(E * (n - 1))
+        else:
+            for _ in range(E):
+                torch.randperm(n)
         return n, rows.astype(np.int32), True
     out = np.empty((E, n, 3), dtype=np.int32)
     for e in range(E):

@@ -240,6 +240,82 @@ def test_kelpie_epoch_draws_match_reference_order():
     assert not changed[:, 1].any() and not (changed[:, 0] & changed[:, 2]).any() and neg2.max() <= 40
 
 
+def test_native_replay_reproduces_torch_and_numpy_generators():
+    """kp_host_rng.cu (kp_mt19937_words / kp_replay_transe_corruptions / kp_replay_numpy_shuffles) against the generators
+    themselves: same numbers as the reference's per-epoch calls (pairwise_ranking_optimizer.py:167-172,
+    multiclass_nll_optimizer.py:148) and both generators left where those calls leave them."""
+    import torch
+    from kelpie_b200 import plans
+    assert plans.HostReplay.available()
+    for seed, E, n, ratio, high in [(0, 65, 4, 5, 24621), (1, 59, 130, 5, 96001), (2, 3, 700, 5, 2), (3, 7, 1, 1, (1 << 28) - 1),
+                                    (4, 2, 1300, 5, 1000001)]:
+        m = ratio * n
+        np.random.seed(seed); torch.manual_seed(seed)
+        torch.rand(1, seed + 1)                       # not at a block boundary
+        perm = plans.HostReplay.numpy_shuffles(E, n)
+        code = plans.HostReplay.transe_corruptions(E, m, n, high)
+        plans.HostReplay.torch_skip(3 * (n - 1))
+        tails = torch.rand(4), np.random.random(3)
+        np.random.seed(seed); torch.manual_seed(seed)
+        torch.rand(1, seed + 1)
+        idx = np.arange(n)
+        for e in range(E):
+            np.random.shuffle(idx)
+            assert np.array_equal(perm[e], idx)
+            rnd = torch.randint(high, (m,)).numpy()[:n]
+            coin = torch.randint(2, (m,)).numpy()[:n]
+            assert np.array_equal(code[e * n:(e + 1) * n].view(np.uint32), (rnd | (coin << 31)).astype(np.uint32))
+        for _ in range(3):
+            torch.randperm(n)
+        assert torch.equal(tails[0], torch.rand(4)) and np.array_equal(tails[1], np.random.random(3))
+
+
+def test_native_replay_and_per_call_draws_agree():
+    """plans.draw_transe_compact / draw_complex: the native replay and the per-call path give the same tables and leave
+    the same generator states, job after job (what a candidate batch does)."""
+    import torch
+    from kelpie_b200 import plans
+    rng = np.random.default_rng(3)
+    jobs = [np.stack([rng.integers(0, 40, t), rng.integers(0, 3, t), rng.integers(0, 40, t)], 1) for t in (1, 2, 11, 64, 300)]
+    hp = dict(epochs=9, negative_triples_ratio=5, batch_size=512)
+
+    def run(native):
+        saved = plans.HostReplay._ok
+        plans.HostReplay._ok = native
+        try:
+            np.random.seed(11); torch.manual_seed(11)
+            out = []
+            for f in jobs:
+                out.append(torch.rand(1, 8).numpy())
+                out.extend(np.asarray(x) for x in plans.draw_transe_compact(f, 3, 41, hp))
+                out.extend(np.asarray(x) for x in plans.draw_complex(f, 3, hp))   # t = 300: 600 rows > batch size
+            out.extend([torch.rand(3).numpy(), np.random.random(3)])
+            return out
+        finally:
+            plans.HostReplay._ok = saved
+
+    a, b = run(True), run(False)
+    assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+
+
+def test_mt19937_words_match_numpy_bit_generator():
+    from kelpie_b200 import runtime
+    lib = runtime.load_library()
+    bg = np.random.MT19937(2024)
+    st = bg.state["state"]
+    key, pos = st["key"].astype(np.uint32).copy(), np.array([st["pos"]], np.int32)
+    out = np.empty(2000, np.uint32)
+    assert lib.kp_mt19937_words(key.ctypes.data, pos.ctypes.data, 2000, out.ctypes.data) == 0
+    assert np.array_equal(out, bg.random_raw(2000).astype(np.uint32))
+    assert lib.kp_mt19937_words(key.ctypes.data, pos.ctypes.data, 1500, None) == 0    # skip only
+    bg.random_raw(1500)
+    assert lib.kp_mt19937_words(key.ctypes.data, pos.ctypes.data, 10, out.ctypes.data) == 0
+    assert np.array_equal(out[:10], bg.random_raw(10).astype(np.uint32))
+    bad = np.array([625], np.int32)
+    assert lib.kp_mt19937_words(key.ctypes.data, bad.ctypes.data, 1, out.ctypes.data) < 0
+    assert lib.kp_replay_transe_corruptions(key.ctypes.data, pos.ctypes.data, 1, 5, 6, 10, out.ctypes.data) < 0  # used > drawn
+
+
 def test_dataset_edits_follow_reference_semantics():
     """dataset.py:242-280: add / remove keep train array, per-entity lists, degrees and the DIRECT filter key."""
     from kelpie_b200.data import Dataset

@@ -15,6 +15,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--preds", type=int, default=20)
 ap.add_argument("--models", default="TransE,ComplEx")
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--repeat", type=int, default=1, help="timed passes over the predictions (same seeds); the best is reported")
 a = ap.parse_args()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ds = Dataset.from_npz(os.path.join(ROOT, "tests", "golden", "dbpedia50_ids.npz"), name="DBpedia50")
@@ -44,14 +45,19 @@ for kind in a.models.split(","):
     if a.profile:
         import cProfile, pstats
         pr = cProfile.Profile(); pr.enable()
-    n_rel, t0 = 0, time.perf_counter()
-    for pred in preds:
-        eng.set_cache()
-        out = builder.build_explanations(pred, ds.entity_to_training_triples[pred[0]])
-        n_rel += out["#relevances"]
-    torch.cuda.synchronize()
-    dt = time.perf_counter() - t0
+    times = []
+    for _ in range(a.repeat):
+        torch.manual_seed(1); np.random.seed(1)
+        n_rel, t0 = 0, time.perf_counter()
+        for pred in preds:
+            eng.set_cache()
+            out = builder.build_explanations(pred, ds.entity_to_training_triples[pred[0]])
+            n_rel += out["#relevances"]
+        torch.cuda.synchronize()
+        times.append(time.perf_counter() - t0)
+    dt = min(times)
     if a.profile:
         pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
-    print(json.dumps({"model": kind, "predictions": len(preds), "relevances": n_rel, "seconds": dt,
+    print(json.dumps({"model": kind, "predictions": len(preds), "relevances": n_rel, "seconds": dt, "passes": [round(t, 4) for t in times],
+                      "host_replay": os.environ.get("KELPIE_HOST_REPLAY", "1"),
                       "candidates_per_s": n_rel / dt, "ms_per_prediction": 1e3 * dt / len(preds)}))
