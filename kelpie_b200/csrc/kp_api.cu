@@ -28,6 +28,14 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->force_simt = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_min_rows")) {
+    ctx->umma_min_rows = value < 1 ? 1 : value;
+    return KP_OK;
+  }
+  if (!strcmp(name, "cx_merge")) {
+    ctx->cx_merge = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "umma_2sm")) {
     ctx->umma_2sm = value;
     return KP_OK;

@@ -47,6 +47,40 @@ __global__ void cx_lse(int G, int n_strips, const float* __restrict__ pm, const 
   lse[g] = M + logf(L);
 }
 
+// Strips of row g folded into strip 0 in place (same order and weights as a sequential merge): one CTA per row, so the
+// per-candidate update below walks one strip per row instead of n_strips (it runs one CTA per candidate; with a
+// handful of candidates per batch -- the explain path -- the serial merge was 57 % of the device time).
+constexpr int MRG_THREADS = 128;
+__global__ void __launch_bounds__(MRG_THREADS) cx_merge_strips(int GA, int D, int n_strips, float* __restrict__ pm,
+                                                              float* __restrict__ pl, float* __restrict__ pO) {
+  extern __shared__ float wgt[];  // [n_strips] e^{m_s - M}, < 0 = empty strip
+  const int g = blockIdx.x, tid = threadIdx.x;
+  float M = -INFINITY;
+  for (int s = 0; s < n_strips; ++s) M = fmaxf(M, pm[(size_t)s * GA + g]);
+  for (int s = tid; s < n_strips; s += MRG_THREADS) {
+    const float ms = pm[(size_t)s * GA + g];
+    wgt[s] = (ms != -INFINITY) ? expf(ms - M) : -1.f;
+  }
+  __syncthreads();
+  for (int k = tid; k < D; k += MRG_THREADS) {
+    float ok = 0.f;
+    for (int s = 0; s < n_strips; ++s) {
+      const float w = wgt[s];
+      if (w >= 0.f) ok += pO[((size_t)s * GA + g) * D + k] * w;
+    }
+    pO[(size_t)g * D + k] = ok;
+  }
+  if (tid == 0) {
+    float L = 0.f;
+    for (int s = 0; s < n_strips; ++s) {
+      const float w = wgt[s];
+      if (w >= 0.f) L += pl[(size_t)s * GA + g] * w;
+    }
+    pm[g] = M;
+    pl[g] = L;
+  }
+}
+
 struct CxUpd {
   int C, N, D, GA, n_strips, optimizer;
   long long step;  // 1-based optimiser step (Adam bias correction)
@@ -272,6 +306,11 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       cx_build_queries<<<(int)((GA + 7) / 8), 256, 0, st>>>((int)GA, D, ctx->ent, ctx->rel, mim, pl.a_cand, nullptr, pl.a_rel, qA);
       KP_LAUNCHED(ctx, 1);
       if ((rc = kp_flash_run(ctx, qA, (int)GA, KP_FLASH_SOFTMAX, pm, plv, pO, st, &ns)) != KP_OK) return rc;
+    }
+    if (GA > 0 && ns > 1 && ctx->cx_merge) {
+      cx_merge_strips<<<(int)GA, MRG_THREADS, (size_t)ns * sizeof(float), st>>>((int)GA, D, ns, pm, plv, pO);
+      KP_LAUNCHED(ctx, 1);
+      ns = 1;
     }
     if (GA + GB > 0) {
       CxUpd u;

@@ -314,7 +314,7 @@ int encode_bf16(kp_ctx* ctx, CUtensorMap* map, const void* base, long long rows,
 }  // namespace
 
 bool kp_flash_umma_usable(kp_ctx* ctx, int G) {
-  return !ctx->force_simt && G >= 32 && ctx->D <= 512 && ctx->D % 4 == 0;
+  return !ctx->force_simt && G >= ctx->umma_min_rows && ctx->D <= 512 && ctx->D % 4 == 0;
 }
 
 namespace {

@@ -71,6 +71,9 @@ struct kp_ctx {
   int64_t launches = 0;
   int64_t rank_rechecks = 0;  // pairs the tensor-core rank pass handed to the exact re-check so far
   int64_t force_simt = 0;
+  int64_t cx_merge = 1;       // ComplEx: strips merged per row by cx_merge_strips before the per-candidate update
+  int64_t umma_min_rows = 1;  // fused pass on tcgen05 from this many rows on (one 128-row tile costs the same for 1..128 rows:
+                              // 43 us vs 164 us for the CUDA-core pass at 24 620 x 400); 32 = the earlier threshold
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
   int64_t umma_x4 = 1;   // rows wider than 256 floats: clusters of two pairs that compute S once (kp_flash_umma4.cu)

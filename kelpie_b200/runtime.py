@@ -203,6 +203,10 @@ class Context:
             raise RuntimeError(f"kp_ctx_create failed ({rc}): {self.lib.kp_last_error(None).decode()}")
         self.handle = handle
         self.has_filter = False
+        # A/B knobs for measurements: KELPIE_B200_OPTS="umma_min_rows=32,cx_merge=0" (kp_set_option names)
+        for kv in filter(None, os.environ.get("KELPIE_B200_OPTS", "").split(",")):
+            name, value = kv.split("=")
+            self.set_option(name.strip(), int(value))
 
     def close(self):
         if getattr(self, "handle", None):
