@@ -64,9 +64,15 @@ __global__ void __launch_bounds__(MRG_THREADS) cx_merge_strips(int GA, int D, in
   __syncthreads();
   for (int k = tid; k < D; k += MRG_THREADS) {
     float ok = 0.f;
-    for (int s = 0; s < n_strips; ++s) {
-      const float w = wgt[s];
-      if (w >= 0.f) ok += pO[((size_t)s * GA + g) * D + k] * w;
+    for (int s0 = 0; s0 < n_strips; s0 += 8) {  // 8 partials in flight per thread, folded in strip order
+      float v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (s0 + j < n_strips) ? pO[((size_t)(s0 + j) * GA + g) * D + k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float w = (s0 + j < n_strips) ? wgt[s0 + j] : -1.f;
+        if (w >= 0.f) ok += v[j] * w;
+      }
     }
     pO[(size_t)g * D + k] = ok;
   }

@@ -103,7 +103,7 @@ class KelpieDataset:
     def undo_removal(self):
         if self.last_removed_triples_number <= 0:
             raise Exception("No removal to undo.")
-        self.kelpie_training_triples = copy.deepcopy(self.kelpie_training_triples_copy)
+        self.kelpie_training_triples = list(self.kelpie_training_triples_copy)  # rows are immutable tuples
         for k, xs in self.last_filter_removals.items():
             for x in xs:
                 self.to_filter.own(k).append(x)
@@ -114,7 +114,7 @@ class KelpieDataset:
     def undo_addition(self):
         if self.last_added_triples_number <= 0:
             raise Exception("No addition to undo.")
-        self.kelpie_training_triples = copy.deepcopy(self.kelpie_training_triples_copy)
+        self.kelpie_training_triples = list(self.kelpie_training_triples_copy)
         for k, xs in self.last_filter_additions.items():
             for x in xs:
                 self.to_filter.own(k).remove(x)

@@ -27,7 +27,7 @@ import time
 import numpy as np
 import torch
 
-from .. import key
+from .. import key, plans
 
 
 def _snapshot():
@@ -39,7 +39,10 @@ def _snapshot():
 
 def _restore(state):
     torch.set_rng_state(state[0])
-    np.random.set_state(state[1])
+    if isinstance(state[1], bytes):  # the engine's cheap copy of the generator words (plans.HostReplay.numpy_snapshot)
+        plans.HostReplay.numpy_restore(state[1])
+    else:
+        np.random.set_state(state[1])
     if len(state) > 2:
         torch.cuda.set_rng_state(state[2])
 

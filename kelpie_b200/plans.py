@@ -6,6 +6,7 @@ EXACTLY the order the reference's Kelpie*Optimizer does 
 index tables the CUDA kernels read, so that a batch of jobs drawn one after the other
 reproduces the reference's sequential run.
 """
+import ctypes
 import os
 from collections import defaultdict
 
@@ -103,6 +104,19 @@ class HostReplay:
         return perm
 
     @classmethod
+    def numpy_snapshot(cls):
+        """The global RandomState's generator words + position as bytes (a 2.5 KB copy instead of the 80 us
+        np.random.get_state() tuple); the legacy Gaussian cache is not part of it -- nothing on this path draws normals
+        from numpy between a snapshot and its restore."""
+        if cls._np_addr is None:
+            cls.numpy_shuffles(0, 0)  # resolves the state address
+        return ctypes.string_at(cls._np_addr, 4 * cls._N + 4)
+
+    @classmethod
+    def numpy_restore(cls, raw):
+        ctypes.memmove(cls._np_addr, raw, 4 * cls._N + 4)
+
+    @classmethod
     def available(cls):
         if cls._ok is None and os.environ.get("KELPIE_HOST_REPLAY") == "0":  # A/B switch: per-call draws
             cls._ok = False
@@ -118,8 +132,11 @@ class HostReplay:
                     code = cls.transe_corruptions(3, 700, 650, 24621)
                     cls.torch_skip(2 * 9)
                     tail_t = torch.rand(5)
+                    snap = cls.numpy_snapshot()
                     perm = cls.numpy_shuffles(3, 37)
                     tail_n = np.random.random(3)
+                    cls.numpy_restore(snap)
+                    ok = ok and np.array_equal(perm, cls.numpy_shuffles(3, 37)) and np.array_equal(tail_n, np.random.random(3))
                     torch.set_rng_state(start_t)
                     np.random.set_state(start_n)
                     for e in range(3):
@@ -316,8 +333,19 @@ class Batch:
             self.pos_ids.append(ids)
         self.statics.append(static)
         self.rows_per_epoch.append(n)
-        self.init_rows.append(np.asarray(init_row, dtype=np.float32).reshape(-1))
+        if isinstance(init_row, torch.Tensor) and init_row.is_cuda:  # drawn on the device (TransE's xavier_normal_): stays there
+            self.init_rows.append(init_row.detach().to(torch.float32).reshape(-1))
+        else:
+            self.init_rows.append(np.asarray(init_row, dtype=np.float32).reshape(-1))
         return len(self.init_rows) - 1
+
+    def _stacked_init_rows(self):
+        """[C, D] fp32: numpy when every row came from the host, one device tensor when any was drawn on the device."""
+        dev = [r for r in self.init_rows if isinstance(r, torch.Tensor)]
+        if not dev:
+            return np.stack(self.init_rows).astype(np.float32)
+        d = dev[0].device
+        return torch.stack([r if isinstance(r, torch.Tensor) else torch.from_numpy(r).to(d) for r in self.init_rows])
 
     def arrays(self, compact=False):
         """Flat arrays of kp_pt_batch (keyword arguments of runtime.Context.post_train).  compact (TransE only): the
@@ -333,7 +361,7 @@ class Batch:
         row_off = np.zeros(len(sizes) + 1, dtype=np.int64)
         row_off[1:] = np.cumsum(sizes)
         out = dict(
-            init_rows=np.stack(self.init_rows).astype(np.float32),
+            init_rows=self._stacked_init_rows(),
             row_off=row_off,
             rows_per_epoch=np.array(self.rows_per_epoch, dtype=np.int32),
             pos=_concat(self.pos, np.int32) if sum(sizes) else np.zeros((1, 3), np.int32),
@@ -352,7 +380,7 @@ class Batch:
         row_off = np.zeros(len(sizes) + 1, dtype=np.int64)
         row_off[1:] = np.cumsum(sizes)
         out = dict(
-            init_rows=np.stack(self.init_rows).astype(np.float32),
+            init_rows=self._stacked_init_rows(),
             row_off=row_off,
             rows_per_epoch=np.array(self.rows_per_epoch, dtype=np.int32),
             static_epochs=False,

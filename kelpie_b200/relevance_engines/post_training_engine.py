@@ -59,7 +59,7 @@ class PostTrainingEngine(RelevanceEngine):
         if name == "TransE":
             row = init_tensor.clone().to(self.rng_device)
             torch.nn.init.xavier_normal_(row)
-            return row.cpu().numpy()
+            return row if row.is_cuda else row.numpy()  # a device draw stays on the device: no D2H sync per candidate
         if name == "ComplEx":
             return (init_tensor.clone() * self.model.init_scale).numpy()
         if self.replay_constructor_rng:
@@ -75,7 +75,7 @@ class PostTrainingEngine(RelevanceEngine):
     # ---- batched core ---------------------------------------------------------------------
     @staticmethod
     def _rng_snapshot():
-        state = [torch.get_rng_state(), np.random.get_state()]
+        state = [torch.get_rng_state(), plans.HostReplay.numpy_snapshot() if plans.HostReplay.available() else np.random.get_state()]
         if torch.cuda.is_available() and torch.cuda.is_initialized():
             state.append(torch.cuda.get_rng_state())
         return state
