@@ -32,6 +32,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_min_rows = value < 1 ? 1 : value;
     return KP_OK;
   }
+  if (!strcmp(name, "skinny_fc")) {
+    ctx->skinny_fc = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "cx_merge")) {
     ctx->cx_merge = value;
     return KP_OK;

@@ -188,6 +188,7 @@ int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size
   const kp_umma_b& B = forward ? ctx->cv.fc_fwd : ctx->cv.fc_bwd;
   if (ctx->umma_fc && !ctx->force_simt && B.ready && M >= 128)
     return kp_gemm_umma(ctx, A, forward ? hidden : D, M, B, C, forward ? D : hidden, ws_offset, st);
+  if (forward && M < 128 && ctx->skinny_fc) return kp_sgemm_skinny_nt(ctx, M, D, hidden, A, hidden, ctx->cv.fc_w, hidden, C, D, st);
   if (forward) return kp_sgemm(ctx, true, M, D, hidden, A, hidden, ctx->cv.fc_w, hidden, C, D, st);
   return kp_sgemm(ctx, false, M, hidden, D, A, D, ctx->cv.fc_w, hidden, C, hidden, st);
 }

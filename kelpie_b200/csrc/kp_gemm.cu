@@ -94,7 +94,72 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
   }
 }
 
+// Skinny C[M, N] = A[M, K] B[N, K]^T for a handful of rows and a long K (the Linear layer's forward for the few
+// (s, p) pairs of an explain-path batch: M ~ 10, N = 200, K = 9728).  The tiled kernel above gives such a product
+// ceil(N / 64) = 4 CTAs that walk K serially (860 us); here a CTA owns 8 rows x 4 columns, its 256 threads stride K
+// with 128-bit loads and the partial sums are folded in a fixed order (shuffles, then the 8 warps in order), so the
+// result is reproducible run to run -- unlike an atomic split-K.
+constexpr int SK_THREADS = 256, SK_ROWS = 8, SK_COLS = 4;
+__global__ void __launch_bounds__(SK_THREADS) skinny_nt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
+                                                               const float* __restrict__ B, int ldb, float* __restrict__ C,
+                                                               int ldc) {
+  __shared__ float red[SK_THREADS / 32][SK_ROWS * SK_COLS];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int n0 = blockIdx.x * SK_COLS, m0 = blockIdx.y * SK_ROWS;
+  float acc[SK_ROWS][SK_COLS];
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+    for (int c = 0; c < SK_COLS; ++c) acc[r][c] = 0.f;
+  for (int k = tid * 4; k < K; k += SK_THREADS * 4) {
+    float4 b[SK_COLS];
+#pragma unroll
+    for (int c = 0; c < SK_COLS; ++c)
+      b[c] = (n0 + c < N) ? *reinterpret_cast<const float4*>(B + (size_t)(n0 + c) * ldb + k) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < SK_ROWS; ++r) {
+      if (m0 + r >= M) break;
+      const float4 a = *reinterpret_cast<const float4*>(A + (size_t)(m0 + r) * lda + k);
+#pragma unroll
+      for (int c = 0; c < SK_COLS; ++c) {
+        acc[r][c] = __fmaf_rn(a.x, b[c].x, acc[r][c]);
+        acc[r][c] = __fmaf_rn(a.y, b[c].y, acc[r][c]);
+        acc[r][c] = __fmaf_rn(a.z, b[c].z, acc[r][c]);
+        acc[r][c] = __fmaf_rn(a.w, b[c].w, acc[r][c]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < SK_ROWS; ++r)
+#pragma unroll
+    for (int c = 0; c < SK_COLS; ++c) {
+      float v = acc[r][c];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if (lane == 0) red[warp][r * SK_COLS + c] = v;
+    }
+  __syncthreads();
+  if (tid < SK_ROWS * SK_COLS) {
+    float sum = 0.f;
+#pragma unroll
+    for (int w = 0; w < SK_THREADS / 32; ++w) sum += red[w][tid];
+    const int m = m0 + tid / SK_COLS, n = n0 + tid % SK_COLS;
+    if (m < M && n < N) C[(size_t)m * ldc + n] = sum;
+  }
+}
+
 }  // namespace
+
+int kp_sgemm_skinny_nt(kp_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       cudaStream_t st) {
+  if (M <= 0 || N <= 0) return KP_OK;
+  if (K % 4 != 0 || lda % 4 != 0 || ldb % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "skinny GEMM needs K and leading dimensions multiple of 4");
+  dim3 grid((N + SK_COLS - 1) / SK_COLS, (M + SK_ROWS - 1) / SK_ROWS);
+  KpTimer timer(ctx, kp_ctx::T_CONV, st);
+  skinny_nt_kernel<<<grid, SK_THREADS, 0, st>>>(M, N, K, A, lda, B, ldb, C, ldc);
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}
 
 int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
              int ldc, cudaStream_t st, int k_rows_b, bool split_k) {

@@ -71,6 +71,7 @@ struct kp_ctx {
   int64_t launches = 0;
   int64_t rank_rechecks = 0;  // pairs the tensor-core rank pass handed to the exact re-check so far
   int64_t force_simt = 0;
+  int64_t skinny_fc = 1;      // ConvE Linear forward of < 128 rows on the skinny kernel (else the tiled CUDA-core GEMM)
   int64_t cx_merge = 1;       // ComplEx: strips merged per row by cx_merge_strips before the per-candidate update
   int64_t umma_min_rows = 1;  // fused pass on tcgen05 from this many rows on (one 128-row tile costs the same for 1..128 rows:
                               // 43 us vs 164 us for the CUDA-core pass at 24 620 x 400); 32 = the earlier threshold
@@ -205,6 +206,9 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
                          int step = 0);
 // k_rows_b (non-transposed B only): rows of B that exist when K was rounded up over a zero-padded A (-1: K);
 // split_k: allow cutting a long K over blockIdx.z (atomic reduction: unordered sums, only for the trainers)
+// C[M, N] = A[M, K] B[N, K]^T for few rows and a long K: K strided over the threads of a CTA, fixed-order reduction
+int kp_sgemm_skinny_nt(kp_ctx* ctx, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C, int ldc,
+                       cudaStream_t st);
 int kp_sgemm(kp_ctx* ctx, bool transb, int M, int N, int K, const float* A, int lda, const float* B, int ldb, float* C,
              int ldc, cudaStream_t st, int k_rows_b = -1, bool split_k = false);
 int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,

@@ -21,7 +21,10 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ds = Dataset.from_npz(os.path.join(ROOT, "tests", "golden", "dbpedia50_ids.npz"), name="DBpedia50")
 CFG = {"TransE": (dict(dimension=256, norm=2), dict(batch_size=2048, epochs=65, lr=0.01, margin=5, negative_triples_ratio=5, regularizer_weight=1.0), 0.35),
        "ComplEx": (dict(dimension=200, init_scale=1e-3), dict(optimizer_name="Adagrad", batch_size=512, epochs=43, lr=0.043, decay1=0.9, decay2=0.999,
-                                                              regularizer_name="N3", regularizer_weight=0), 0.25)}
+                                                              regularizer_name="N3", regularizer_weight=0), 0.25),
+       # configs/ConvE_DBpedia50_explanation.json
+       "ConvE": (dict(dimension=200, input_dropout_rate=0.0, feature_map_dropout_rate=0.0, hidden_dropout_rate=0.0, hidden_layer_size=9728),
+                 dict(batch_size=512, label_smoothing=0.1, lr=0.018, decay=0.995, epochs=69), 0.2)}
 preds = []
 for s, p, o in ds.testing_triples:
     if 3 <= len(ds.entity_to_training_triples[s]) <= 20:
@@ -31,7 +34,8 @@ for s, p, o in ds.testing_triples:
 for kind in a.models.split(","):
     params, hp, scale = CFG[kind]
     cls = MODEL_REGISTRY[kind]["class"]
-    m = cls(ds, cls.get_hyperparams_class()(**params), init_random=False)
+    torch.manual_seed(7)
+    m = cls(ds, cls.get_hyperparams_class()(**params), init_random=(kind == "ConvE"))  # ConvE: torch's default layer init
     g = torch.Generator().manual_seed(1)
     with torch.no_grad():
         m.entity_embeddings.copy_(torch.randn(m.entity_embeddings.shape, generator=g) * scale)
