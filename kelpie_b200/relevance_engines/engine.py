@@ -22,25 +22,25 @@ class RelevanceEngine:
         """engine.py:62-124: eligible heads e whose (e,p,o) is not already filtered-rank 1."""
         s, p, o = pred
         ds = self.dataset
+        # engine.py:70-88 (host eligibility rules), one pass with the lookups hoisted out of the loop
+        degree, to_filter = ds.entity_to_degree, ds.to_filter
+        functional = ds.relation_to_type[p] in [ONE_TO_ONE, MANY_TO_ONE]
+        cap = degree_cap if degree_cap else float("inf")
+        heads = self.o_to_training_triples if criage else None
         entities = []
-        for entity in range(ds.num_entities):  # engine.py:70-88 (host eligibility rules)
-            if entity == s:
+        for entity in range(ds.num_entities):
+            if entity == s or not (1 <= degree[entity] <= cap):
                 continue
-            if ds.entity_to_degree[entity] < 1:
+            if heads is not None and entity not in heads:
                 continue
-            if degree_cap and ds.entity_to_degree[entity] > degree_cap:
+            key = (entity, p)
+            if key in to_filter and (functional or o in to_filter[key]):
                 continue
-            if criage and entity not in self.o_to_training_triples:
-                continue
-            if (entity, p) in ds.to_filter:
-                if ds.relation_to_type[p] in [ONE_TO_ONE, MANY_TO_ONE]:
-                    continue
-                if o in ds.to_filter[(entity, p)]:
-                    continue
             entities.append(entity)
         if len(entities) == 0:
             return []
-        triples = np.array([(e, p, o) for e in entities], dtype=np.int64)
+        triples = np.empty((len(entities), 3), dtype=np.int64)
+        triples[:, 0], triples[:, 1], triples[:, 2] = entities, p, o
         ctx = context_for(self.model)
         mode = runtime.RANK_MODEL
         ts, _, _, cnt = ctx.filtered_rank(triples, mode, counters=True)

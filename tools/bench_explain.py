@@ -3,18 +3,19 @@ stochastic_builder.py:102-107): StochasticBuilder over test predictions of the r
 necessary mode, candidates = the head's training facts (the top-20 cut of the topology prefilter for these degrees),
 seeded stand-in weights.  Every host cost is inside the clock: KelpieDataset overlays, plan drawing in the reference's
 RNG order, uploads, kernels, result readback, the builder's control flow.  Prints one JSON line per model."""
-import sys, os, json, time, argparse
+import sys, os, json, time, argparse, random
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from kelpie_b200.data import Dataset
 from kelpie_b200.link_prediction import MODEL_REGISTRY
-from kelpie_b200.relevance_engines import NecessaryPostTrainingEngine
+from kelpie_b200.relevance_engines import NecessaryPostTrainingEngine, SufficientPostTrainingEngine
 from kelpie_b200.explanation_builders import StochasticBuilder
 
 ap = argparse.ArgumentParser()
 ap.add_argument("--preds", type=int, default=20)
 ap.add_argument("--models", default="TransE,ComplEx")
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--mode", default="necessary", choices=["necessary", "sufficient"], help="sufficient: 10 conversions, degree cap 200 (configs[1])")
 ap.add_argument("--repeat", type=int, default=1, help="timed passes over the predictions (same seeds); the best is reported")
 a = ap.parse_args()
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,27 +42,34 @@ for kind in a.models.split(","):
         m.entity_embeddings.copy_(torch.randn(m.entity_embeddings.shape, generator=g) * scale)
         m.relation_embeddings.copy_(torch.randn(m.relation_embeddings.shape, generator=g) * scale)
     m.eval()
-    eng = NecessaryPostTrainingEngine(m, ds, hp)
-    builder = StochasticBuilder(xsi=5.0, engine=eng, max_explanation_length=4)
+    suff = a.mode == "sufficient"
+    eng = (SufficientPostTrainingEngine if suff else NecessaryPostTrainingEngine)(m, ds, hp)
+    builder = StochasticBuilder(xsi=0.9 if suff else 5.0, engine=eng, max_explanation_length=4)
+
+    def explain(pred):
+        if suff:  # pipeline.py:39 -- the conversion set is part of every prediction's cost
+            eng.select_entities_to_convert(pred, 10, 200)
+        return builder.build_explanations(pred, ds.entity_to_training_triples[pred[0]])
+
     torch.manual_seed(0); np.random.seed(0)
-    builder.build_explanations(preds[0], ds.entity_to_training_triples[preds[0][0]])  # warm-up: context, split tables
+    explain(preds[0])  # warm-up: context, split tables
     torch.cuda.synchronize()
     if a.profile:
         import cProfile, pstats
         pr = cProfile.Profile(); pr.enable()
     times = []
     for _ in range(a.repeat):
-        torch.manual_seed(1); np.random.seed(1)
+        torch.manual_seed(1); np.random.seed(1); random.seed(1)
         n_rel, t0 = 0, time.perf_counter()
         for pred in preds:
             eng.set_cache()
-            out = builder.build_explanations(pred, ds.entity_to_training_triples[pred[0]])
+            out = explain(pred)
             n_rel += out["#relevances"]
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     dt = min(times)
     if a.profile:
         pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
-    print(json.dumps({"model": kind, "predictions": len(preds), "relevances": n_rel, "seconds": dt, "passes": [round(t, 4) for t in times],
+    print(json.dumps({"model": kind, "mode": a.mode, "predictions": len(preds), "relevances": n_rel, "seconds": dt, "passes": [round(t, 4) for t in times],
                       "host_replay": os.environ.get("KELPIE_HOST_REPLAY", "1"),
                       "candidates_per_s": n_rel / dt, "ms_per_prediction": 1e3 * dt / len(preds)}))
