@@ -126,7 +126,7 @@ class HostReplay:
                 ok = True
                 for seed in (None, 12345):  # the live states, and freshly seeded ones
                     if seed is not None:
-                        torch.manual_seed(seed)
+                        torch.default_generator.manual_seed(seed)  # the CPU generator only: torch.manual_seed reseeds CUDA's too
                         np.random.seed(seed)
                     start_t, start_n = torch.get_rng_state(), np.random.get_state()
                     code = cls.transe_corruptions(3, 700, 650, 24621)

@@ -270,6 +270,21 @@ def test_native_replay_reproduces_torch_and_numpy_generators():
         assert torch.equal(tails[0], torch.rand(4)) and np.array_equal(tails[1], np.random.random(3))
 
 
+def test_replay_self_check_restores_the_host_generators():
+    import torch
+    from kelpie_b200 import plans
+    torch.manual_seed(42); np.random.seed(42)
+    torch.rand(3); np.random.random(3)
+    t0, n0 = torch.get_rng_state().clone(), np.random.get_state()
+    saved, plans.HostReplay._ok = plans.HostReplay._ok, None
+    try:
+        assert plans.HostReplay.available()
+    finally:
+        plans.HostReplay._ok = saved if saved is not None else plans.HostReplay._ok
+    n1 = np.random.get_state()
+    assert torch.equal(t0, torch.get_rng_state()) and np.array_equal(n0[1], n1[1]) and n0[2:] == n1[2:]
+
+
 def test_native_replay_and_per_call_draws_agree():
     """plans.draw_transe_compact / draw_complex: the native replay and the per-call path give the same tables and leave
     the same generator states, job after job (what a candidate batch does)."""

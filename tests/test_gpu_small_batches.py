@@ -88,3 +88,20 @@ def test_conve_skinny_linear_forward_matches_tiled_gemm_and_oracle(sizes):
     b = ctx.all_scores(q).cpu().numpy()
     ctx.set_option("skinny_fc", 1)
     assert np.abs(a - b).max() <= 1e-5 * max(np.abs(b).max(), 1e-30)
+
+
+def test_replay_self_check_leaves_every_generator_untouched():
+    """plans.HostReplay.available() runs lazily in the middle of a run (first plan drawn): the CPU, CUDA and numpy
+    generators must come out of it exactly as they went in (the reference's mimic rows are drawn on the CUDA one)."""
+    from kelpie_b200 import plans
+    torch.manual_seed(42); np.random.seed(42)
+    torch.rand(3); torch.rand(3, device="cuda"); np.random.random(3)
+    before = (torch.get_rng_state().clone(), torch.cuda.get_rng_state().clone(), np.random.get_state())
+    saved, plans.HostReplay._ok = plans.HostReplay._ok, None
+    try:
+        assert plans.HostReplay.available()
+    finally:
+        plans.HostReplay._ok = saved if saved is not None else plans.HostReplay._ok
+    assert torch.equal(before[0], torch.get_rng_state()) and torch.equal(before[1], torch.cuda.get_rng_state())
+    after = np.random.get_state()
+    assert np.array_equal(before[2][1], after[1]) and before[2][2:] == after[2:]
