@@ -60,16 +60,17 @@ for kind in a.models.split(","):
     times = []
     for _ in range(a.repeat):
         torch.manual_seed(1); np.random.seed(1); random.seed(1)
-        n_rel, t0 = 0, time.perf_counter()
+        n_rel, checksum, t0 = 0, 0.0, time.perf_counter()
         for pred in preds:
             eng.set_cache()
             out = explain(pred)
             n_rel += out["#relevances"]
+            checksum += sum(float(v) for _, v in out["rule_to_relevance"])
         torch.cuda.synchronize()
         times.append(time.perf_counter() - t0)
     dt = min(times)
     if a.profile:
         pr.disable(); pstats.Stats(pr).sort_stats("cumulative").print_stats(18)
-    print(json.dumps({"model": kind, "mode": a.mode, "predictions": len(preds), "relevances": n_rel, "seconds": dt, "passes": [round(t, 4) for t in times],
+    print(json.dumps({"model": kind, "mode": a.mode, "predictions": len(preds), "relevances": n_rel, "relevance_checksum": round(checksum, 4), "seconds": dt, "passes": [round(t, 4) for t in times],
                       "host_replay": os.environ.get("KELPIE_HOST_REPLAY", "1"),
                       "candidates_per_s": n_rel / dt, "ms_per_prediction": 1e3 * dt / len(preds)}))
