@@ -42,6 +42,7 @@ class HostReplay:
     _ok = None
     _lib = None
     _np_addr = None
+    _np_bg = None
 
     @classmethod
     def lib(cls):
@@ -89,17 +90,25 @@ class HostReplay:
 
     # ---- numpy's legacy global RandomState
     @classmethod
-    def numpy_shuffles(cls, E, n):
-        """[E, n] int32: an index vector after each of E cumulative np.random.shuffle calls."""
-        if cls._np_addr is None:
-            bg = np.random.mtrand._rand._bit_generator
+    def _numpy_addr(cls):
+        """Address of the global RandomState's generator words (624 x u32, then the position); re-resolved if the
+        bit generator object was swapped (np.random.set_bit_generator)."""
+        bg = np.random.mtrand._rand._bit_generator
+        if bg is not cls._np_bg:
             if type(bg).__name__ != "MT19937":
                 raise RuntimeError("numpy's global generator is not an MT19937")
-            cls._np_bg = bg  # keeps the state alive
             addr = bg.ctypes.state_address
-            cls._np_addr = int(getattr(addr, "value", addr))
+            cls._np_bg, cls._np_addr = bg, int(getattr(addr, "value", addr))  # the reference keeps the state alive
+            if cls._ok:  # a generator object the replay has not been checked against yet
+                cls._ok = None
+        return cls._np_addr
+
+    @classmethod
+    def numpy_shuffles(cls, E, n):
+        """[E, n] int32: an index vector after each of E cumulative np.random.shuffle calls."""
+        addr = cls._numpy_addr()
         perm = np.empty((E, n), dtype=np.int32)
-        rc = cls.lib().kp_replay_numpy_shuffles(cls._np_addr, cls._np_addr + 4 * cls._N, E, n, perm.ctypes.data)
+        rc = cls.lib().kp_replay_numpy_shuffles(addr, addr + 4 * cls._N, E, n, perm.ctypes.data)
         assert rc == 0, rc
         return perm
 
@@ -108,16 +117,16 @@ class HostReplay:
         """The global RandomState's generator words + position as bytes (a 2.5 KB copy instead of the 80 us
         np.random.get_state() tuple); the legacy Gaussian cache is not part of it -- nothing on this path draws normals
         from numpy between a snapshot and its restore."""
-        if cls._np_addr is None:
-            cls.numpy_shuffles(0, 0)  # resolves the state address
-        return ctypes.string_at(cls._np_addr, 4 * cls._N + 4)
+        return ctypes.string_at(cls._numpy_addr(), 4 * cls._N + 4)
 
     @classmethod
     def numpy_restore(cls, raw):
-        ctypes.memmove(cls._np_addr, raw, 4 * cls._N + 4)
+        ctypes.memmove(cls._numpy_addr(), raw, 4 * cls._N + 4)
 
     @classmethod
     def available(cls):
+        if cls._ok and np.random.mtrand._rand._bit_generator is not cls._np_bg:
+            cls._ok = None  # numpy's global generator object was swapped since the check
         if cls._ok is None and os.environ.get("KELPIE_HOST_REPLAY") == "0":  # A/B switch: per-call draws
             cls._ok = False
         if cls._ok is None:
