@@ -96,10 +96,10 @@ __global__ void __launch_bounds__(GT) sgemm_kernel(int M, int N, int K, const fl
 
 // Skinny C[M, N] = A[M, K] B[N, K]^T for a handful of rows and a long K (the Linear layer's forward for the few
 // (s, p) pairs of an explain-path batch: M ~ 10, N = 200, K = 9728).  The tiled kernel above gives such a product
-// ceil(N / 64) = 4 CTAs that walk K serially (860 us); here a CTA owns 8 rows x 4 columns, its 256 threads stride K
-// with 128-bit loads and the partial sums are folded in a fixed order (shuffles, then the 8 warps in order), so the
+// ceil(N / 64) = 4 CTAs that walk K serially (860 us); here a CTA owns 8 rows x 4 columns, its threads stride K
+// with 128-bit loads and the partial sums are folded in a fixed order (shuffles, then the warps in order), so the
 // result is reproducible run to run -- unlike an atomic split-K.
-constexpr int SK_THREADS = 256, SK_ROWS = 8, SK_COLS = 4;
+constexpr int SK_THREADS = 512, SK_ROWS = 8, SK_COLS = 4;  // 512 threads: K = 9728 is 4.75 trips of the strided loop
 __global__ void __launch_bounds__(SK_THREADS) skinny_nt_kernel(int M, int N, int K, const float* __restrict__ A, int lda,
                                                                const float* __restrict__ B, int ldb, float* __restrict__ C,
                                                                int ldc) {
