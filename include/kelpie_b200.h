@@ -74,7 +74,7 @@ typedef struct kp_conve_weights {
   float drop_input, drop_feature, drop_hidden; /* conve.py:34-36 */
 } kp_conve_weights;
 
-/* Hyper-parameters of one post-training (the `training` dict of configs/*.json as the
+/* Hyper-parameters of one post-training (the `training` dict of configs/<model>_<dataset>_explanation.json as the
  * reference's Kelpie*Optimizer consumes it). */
 typedef struct kp_hp {
   int32_t epochs;
