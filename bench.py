@@ -386,7 +386,11 @@ def main():
             "roofline": {"bound": work["bound"], "kernel": work["what"], "achieved": achieved, "peak": peak, "unit": unit,
                          "frac": (achieved / peak) if achieved else None, "traffic": traffic, "peak_source": src,
                          "launches_timed": int(dom_n), "avg_launch_ms": (dom_ms / dom_n) if dom_n else None,
-                         "share_of_step": dom_ms / t_kernel if t_kernel else None},
+                         "share_of_step": dom_ms / t_kernel if t_kernel else None,
+                         # fp32 parity on bf16 tensor cores: every product is hi*hi + hi*lo + lo*hi, so the
+                         # tensor pipe executes 3 MMAs per algorithmic one and `frac` cannot exceed 1/3
+                         **({"mma_per_product": 3, "executed_frac": 3 * achieved / peak if achieved else None}
+                            if work["bound"] == "tensor" else {})},
             "kernel_ms_per_step": breakdown,  # CUDA-event time of the library's kernels by category (rank 0)
             "clocks": sampler.summary(w0, w1) if sampler else None,
             "relevance_checksum": float(np.nansum(rel_vals)),
