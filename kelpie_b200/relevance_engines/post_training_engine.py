@@ -57,8 +57,11 @@ class PostTrainingEngine(RelevanceEngine):
     def _init_row(self, init_tensor):
         name = self.model.name
         if name == "TransE":
-            row = init_tensor.clone().to(self.rng_device)
-            torch.nn.init.xavier_normal_(row)
+            # xavier_normal_ of a [1, D] tensor = normal_(0, sqrt(2 / (fan_in + fan_out))) with fan_in = D, fan_out = 1, drawn
+            # on the generator of the row's device; the values of init_tensor are overwritten, so they are not copied over
+            rows, cols = init_tensor.shape
+            row = torch.empty((rows, cols), dtype=init_tensor.dtype, device=self.rng_device)
+            row.normal_(0.0, math.sqrt(2.0 / float(cols + rows)))
             return row if row.is_cuda else row.numpy()  # a device draw stays on the device: no D2H sync per candidate
         if name == "ComplEx":
             return (init_tensor.clone() * self.model.init_scale).numpy()
@@ -128,7 +131,7 @@ class PostTrainingEngine(RelevanceEngine):
 
         def result(j):
             return {"target_score": float(ts[j]), "best_score": torch.tensor(float(bs[j])),
-                    "target_rank": torch.tensor(int(rk[j]))}
+                    "target_rank": torch.tensor(int(rk[j])), "_rank": int(rk[j])}
 
         for pred, j in pending_base.items():
             self.base_pt_results[pred] = result(j)
@@ -147,9 +150,11 @@ class NecessaryPostTrainingEngine(PostTrainingEngine):
         dataset.undo_removal()
 
     def _relevance(self, pt, base):  # post_training_engine.py:136-145
-        rank_worsening = pt["target_rank"] - base["target_rank"]
         score_worsening = (pt["target_score"] - base["target_score"] if self.model.is_minimizer()
                            else base["target_score"] - pt["target_score"])
+        if "_rank" in pt and "_rank" in base:  # int64 tensor + Python float = a float32 sum, without the tensor ops
+            return float(np.float32(pt["_rank"] - base["_rank"]) + np.float32(self.sigmoid(score_worsening)))
+        rank_worsening = pt["target_rank"] - base["target_rank"]
         return float(rank_worsening + self.sigmoid(score_worsening))
 
     def compute_relevance(self, pred, triples):
@@ -169,9 +174,12 @@ class SufficientPostTrainingEngine(PostTrainingEngine):
         dataset.undo_addition()
 
     def _relevance(self, pt, base):  # post_training_engine.py:164-176
-        rank_improvement = base["target_rank"] - pt["target_rank"]
         score_improvement = (base["target_score"] - pt["target_score"] if self.model.is_minimizer()
                              else pt["target_score"] - base["target_score"])
+        if "_rank" in pt and "_rank" in base:  # as above: the float32 sum of the reference's tensor expression
+            relevance = float(np.float32(base["_rank"] - pt["_rank"]) + np.float32(self.sigmoid(score_improvement)))
+            return relevance / float(base["_rank"])
+        rank_improvement = base["target_rank"] - pt["target_rank"]
         relevance = float(rank_improvement + self.sigmoid(score_improvement))
         return relevance / float(base["target_rank"])
 
