@@ -3,6 +3,8 @@
 
 #include <mutex>
 
+#include <stdlib.h>
+
 #include "kp_internal.h"
 
 static std::string g_create_error;
@@ -46,6 +48,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
   }
   if (!strcmp(name, "umma_x4")) {
     ctx->umma_x4 = value;
+    return KP_OK;
+  }
+  if (!strcmp(name, "sv_dbg")) {
+    ctx->sv_dbg = value;
     return KP_OK;
   }
   if (!strcmp(name, "umma_fc")) {
@@ -121,6 +127,14 @@ extern "C" int kp_stat(kp_ctx* ctx, const char* name, double* out) {
   }
   if (!strncmp(name, "umma_prof_", 10) && ctx->umma_prof) {  // slot / own / for / total (MMA-thread cycles, summed over pairs)
     static const char* w[] = {"slot", "own", "for", "total", "send", "wpin", "whdr", "wsfull", "soft"};
+    if (name[10] >= '0' && name[10] <= '9') {  // raw counter by index (kp_flash_umma_sv.cu: S slot, S dep, S total, V slot, V dep, V total)
+      const int i = atoi(name + 10);
+      if (i < 0 || i > 15) KP_FAIL(ctx, KP_EINVAL, "umma_prof index out of range");
+      unsigned long long v = 0;
+      KP_CUDA(ctx, cudaMemcpy(&v, ctx->umma_prof + i, sizeof(v), cudaMemcpyDeviceToHost));
+      *out = (double)v;
+      return KP_OK;
+    }
     for (int i = 0; i < 9; ++i)
       if (!strcmp(name + 10, w[i])) {
         unsigned long long v = 0;

@@ -328,6 +328,7 @@ struct UPlan {
   int n_strips, n_tiles, tps;
   bool pair;   // cta_group::2 kernel (kp_flash_umma2.cu): SM pairs over 2 query tiles
   bool quad;   // clusters of two pairs sharing S across the dim chunks (kp_flash_umma4.cu)
+  bool sv;     // ... with one pair computing S / softmax and the other contracting (kp_flash_umma_sv.cu)
 };
 UPlan umma_plan(kp_ctx* ctx, int G) {
   UPlan u;
@@ -348,13 +349,15 @@ UPlan umma_plan(kp_ctx* ctx, int G) {
   u.n_qt = ((n_qt + cq - 1) / cq) * cq;
   u.n_tiles = (int)((ctx->N + 127) / 128);
   u.quad = u.pair && u.cc == 2 && ctx->umma_x4 != 0;
-  const int sms = u.quad ? kp_flash_umma4_sms(ctx) : ctx->sm_count;
+  u.sv = u.quad && ctx->umma_x4 >= 2;
+  const int sms = u.sv ? kp_flash_umma_sv_sms(ctx) : (u.quad ? kp_flash_umma4_sms(ctx) : ctx->sm_count);
   // Strip count: the entity range is cut into `s` strips so that (query-tile clusters x strips) fills whole waves
   // of the SMs the launch can occupy.  unit = CTAs that must be co-resident, units = clusters per strip.
   const int unit = u.quad ? 4 : (u.pair ? 2 : 1);
   const long long units = ((long long)u.n_qt * u.cc + unit - 1) / unit;
   const int s = kp_plan_strips(units, sms / unit, u.n_tiles);
   u.tps = (u.n_tiles + s - 1) / s;
+  if (u.sv) u.tps = (u.tps + 1) & ~1;  // the S pair scores two entity tiles per MMA
   u.n_strips = (u.n_tiles + u.tps - 1) / u.tps;
   return u;
 }
@@ -442,6 +445,9 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   CUtensorMap qh_map, ql_map;
   if ((rc = kp_umma_split_rows(ctx, qmat, G, (long long)u.n_qt * 128, &qh_map, &ql_map, st)) != KP_OK) return rc;
 
+  if (u.sv)
+    return kp_flash_umma_sv_launch(ctx, qh_map, ql_map, G, u.KBs, u.bpc / 2, u.n_qt, u.n_strips, u.tps, mode, part_m, part_l,
+                                   part_O, st);
   if (u.quad)
     return kp_flash_umma4_launch(ctx, qh_map, ql_map, G, u.KBs, u.bpc / 2, u.n_qt, u.n_strips, u.tps, mode, part_m, part_l,
                                  part_O, st);

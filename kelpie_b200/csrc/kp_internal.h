@@ -77,7 +77,9 @@ struct kp_ctx {
                               // 43 us vs 164 us for the CUDA-core pass at 24 620 x 400); 32 = the earlier threshold
   int64_t force_tile = 0;  // route few-query passes through the 64-query tile kernel (tests)
   int64_t umma_2sm = 1;  // use the cta_group::2 pass when there are >= 2 query tiles
-  int64_t umma_x4 = 1;   // rows wider than 256 floats: clusters of two pairs that compute S once (kp_flash_umma4.cu)
+  int64_t umma_x4 = 2;   // rows wider than 256 floats: clusters of two pairs that compute S once; 2 = one pair scores, the other
+                         // contracts (kp_flash_umma_sv.cu), 1 = both alternate (kp_flash_umma4.cu), 0 = independent pairs
+  int64_t sv_dbg = 0;    // debug switches of kp_flash_umma_sv.cu
   int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
   int64_t umma_rotate = 1;  // rotating start of the entity walk (clusters share the table pass through L2)
@@ -218,6 +220,10 @@ int kp_flash_umma4_sms(kp_ctx* ctx);
 int kp_flash_umma4_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs,
                           int groups_per_chunk, int n_qt, int n_strips, int tps, int mode, float* part_m, float* part_l,
                           float* part_O, cudaStream_t st);
+int kp_flash_umma_sv_sms(kp_ctx* ctx);
+int kp_flash_umma_sv_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs, int ngroup,
+                            int n_qt, int n_strips, int tps, int mode, float* part_m, float* part_l, float* part_O,
+                            cudaStream_t st);
 int kp_umma_tables(kp_ctx* ctx, cudaStream_t st);
 int kp_umma_split_rows(kp_ctx* ctx, const float* mat, int G, long long Gpad, CUtensorMap* hi_map, CUtensorMap* lo_map,
                        cudaStream_t st);

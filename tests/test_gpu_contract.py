@@ -4,8 +4,9 @@ Stated tolerance per row: (2e-5 + 4 * 2^-17 * max_j |q o E_j|_2) of sum_j p_gj (
 sum_j p_gj |E_jk| (O) -- the bf16x3 split keeps ~16 mantissa bits per product (fp32 accumulation), and
 an absolute perturbation of a logit is a relative perturbation of its probability.
 
-Covers the cluster-of-4 kernel (rows wider than 256 floats: S shared between the two dim chunks
-through distributed shared memory), the cta_group::2 pair kernel and the single-CTA kernel, with
+Covers the cluster-of-4 kernels (rows wider than 256 floats: the default one, where one SM pair
+scores and the other contracts, and round 1's, where both alternate; P crosses distributed shared
+memory in both), the cta_group::2 pair kernel and the single-CTA kernel, with
 strips of many entity tiles, a ragged last tile, and logits that grow along the table so that the
 lazy rescale of the TMEM accumulators fires (reference max moves by more than 8)."""
 import numpy as np
@@ -57,7 +58,7 @@ def test_contract_matches_fp64(D, N, G, mode):
     ctx.close()
 
 
-@pytest.mark.parametrize("x4", [1, 0])
+@pytest.mark.parametrize("x4", [2, 1, 0])
 def test_contract_rescale_path(x4):
     """Entity norms grow along the table -> the row max keeps moving up -> O is rescaled in TMEM, by
     the tile's owner and (cluster-of-4 kernel) by the pair that received the tile."""
@@ -75,7 +76,8 @@ def test_contract_rescale_path(x4):
     ctx.close()
 
 
-def test_quad_matches_pair_kernel():
+@pytest.mark.parametrize("quad", [2, 1])
+def test_quad_matches_pair_kernel(quad):
     from kelpie_b200 import runtime
     rng = np.random.default_rng(11)
     N, D, G = 30011, 512, 512
@@ -83,12 +85,12 @@ def test_quad_matches_pair_kernel():
     q = (rng.standard_normal((G, D)) * 0.3).astype(np.float32)
     ctx = runtime.Context("ComplEx", ent, np.zeros((2, D), np.float32))
     out = {}
-    for x4 in (1, 0):
+    for x4 in (quad, 0):
         ctx.set_option("umma_x4", x4)
         m, l, O = ctx.contract(q, 0)
         torch.cuda.synchronize()
         out[x4] = (m.cpu().numpy(), l.cpu().numpy(), O.cpu().numpy())
-    s = np.exp(out[1][0].astype(np.float64) - out[0][0])
-    assert np.abs(out[1][1] * s - out[0][1]).max() <= 1e-5 * np.abs(out[0][1]).max()
-    assert np.abs(out[1][2] * s[:, None] - out[0][2]).max() <= 1e-5 * np.abs(out[0][2]).max()
+    s = np.exp(out[quad][0].astype(np.float64) - out[0][0])
+    assert np.abs(out[quad][1] * s - out[0][1]).max() <= 1e-5 * np.abs(out[0][1]).max()
+    assert np.abs(out[quad][2] * s[:, None] - out[0][2]).max() <= 1e-5 * np.abs(out[0][2]).max()
     ctx.close()

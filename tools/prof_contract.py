@@ -42,4 +42,10 @@ try:
         out["wait_" + k] = ctx.stat("umma_prof_" + k) / max(tot, 1)
 except RuntimeError:
     pass
+try:  # S/V kernel (umma_x4 = 2): MMA-thread cycles of the scoring (S) and contracting (V) pairs
+    n_cl = (a.G + 255) // 256
+    for i, k in enumerate(("s_slot", "s_dep", "s_total", "v_slot", "v_dep", "v_total")):
+        out[k + "_cycles_per_cluster"] = ctx.stat(f"umma_prof_{i}") / (n_cl * a.reps)
+except RuntimeError:
+    pass
 print(out)
