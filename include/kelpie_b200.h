@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define KP_ABI_VERSION 2
+#define KP_ABI_VERSION 3
 
 enum kp_status {
   KP_OK = 0,
@@ -76,6 +76,8 @@ typedef struct kp_conve_weights {
 
 /* Hyper-parameters of one post-training (the `training` dict of configs/<model>_<dataset>_explanation.json as the
  * reference's Kelpie*Optimizer consumes it). */
+typedef enum kp_regularizer { KP_REG_N3 = 0, KP_REG_N2 = 1 } kp_regularizer;
+
 typedef struct kp_hp {
   int32_t epochs;
   int32_t batch_size;
@@ -83,8 +85,9 @@ typedef struct kp_hp {
   float lr;               /* ConvE: the caller passes 1e-3, see bce_optimizer.py:165 */
   float beta1, beta2, eps;
   float margin;           /* TransE pairwise_ranking_optimizer.py:44 */
-  float reg_weight;       /* TransE L2 / ComplEx N3 weight */
+  float reg_weight;       /* TransE L2 / ComplEx N3 or N2 weight */
   float label_smoothing;  /* ConvE bce_optimizer.py:108-110 */
+  int32_t regularizer;    /* ABI 3, ComplEx: a kp_regularizer value -- multiclass_nll_optimizer.py:46-49, regularizers.py:25-46 */
 } kp_hp;
 
 /* One batch of C independent mimic post-trainings (one mimic row per candidate).
@@ -165,6 +168,11 @@ int kp_filter_upload(kp_ctx* ctx, int64_t n_keys, const int64_t* keys, const int
  * Needs N * R2 < 2^31.  kp_filter_download reads the resident CSR back (call with NULL arrays for the sizes). */
 int kp_filter_build(kp_ctx* ctx, int64_t n_facts, const int32_t* facts, void* stream);
 int kp_filter_download(kp_ctx* ctx, int64_t* n_keys, int64_t* n_ids, int64_t* keys, int64_t* offsets, int32_t* ids);
+
+/* Model.score (transe.py:38-46, complex.py:41-56, conve.py:68-75): out[q] = score of (s_q, p_q, o_q) -- Q rows of work,
+ * no pass over the entity table.  Ids equal to N denote the query's own mimic row (mimic_rows [Q, D], nullable). ABI 3. */
+int kp_score_triples(kp_ctx* ctx, int32_t n_queries, const int32_t* triples, const float* mimic_rows, float* out,
+                     void* stream);
 
 /* Model.all_scores (transe.py:48-65, complex.py:88-113, conve.py:133-158):
  * out[q, j] = score of (s_q, p_q, j), row stride out_ld floats, N (+1) columns. */

@@ -7,7 +7,8 @@
 
 #include "kp_internal.h"
 
-static std::string g_create_error;
+// message of a failed kp_ctx_create, read back by the calling thread through kp_last_error(NULL)
+static thread_local std::string g_create_error;
 
 void kp_set_error(kp_ctx* ctx, const char* msg) {
   if (ctx)
@@ -319,11 +320,35 @@ extern "C" int kp_ctx_destroy(kp_ctx* ctx) {
   return KP_OK;
 }
 
+// The resident CSR is replaced, not accumulated: the previous arrays are freed once no kernel can still read them.
+void kp_filter_release(kp_ctx* ctx) {
+  void* old[3] = {ctx->f_keys, ctx->f_off, ctx->f_ids};
+  if (!old[0] && !old[1] && !old[2]) return;
+  cudaDeviceSynchronize();
+  for (int i = 0; i < 3; ++i) {
+    void* p = old[i];
+    bool dup = !p;
+    for (int j = 0; j < i; ++j) dup = dup || old[j] == p;  // the empty CSR aliases one buffer
+    if (dup) continue;
+    for (size_t k = 0; k < ctx->owned.size(); ++k)
+      if (ctx->owned[k] == p) {
+        ctx->owned.erase(ctx->owned.begin() + k);
+        cudaFree(p);
+        break;
+      }
+  }
+  ctx->f_keys = nullptr;
+  ctx->f_off = nullptr;
+  ctx->f_ids = nullptr;
+  ctx->n_keys = 0;
+}
+
 extern "C" int kp_filter_upload(kp_ctx* ctx, int64_t n_keys, const int64_t* keys, const int64_t* offsets,
                                 const int32_t* objs) {
   if (!ctx) return KP_EINVAL;
   if (n_keys < 0 || (n_keys > 0 && (!keys || !offsets))) KP_FAIL(ctx, KP_EINVAL, "bad filter CSR arguments");
   KP_CUDA(ctx, cudaSetDevice(ctx->device));
+  kp_filter_release(ctx);
   int64_t total = 0;
   if (n_keys > 0) KP_CUDA(ctx, cudaMemcpy(&total, offsets + n_keys, sizeof(int64_t), cudaMemcpyDefault));
   if (total < 0 || (total > 0 && !objs)) KP_FAIL(ctx, KP_EINVAL, "bad filter CSR offsets");
@@ -346,6 +371,15 @@ extern "C" int kp_all_scores(kp_ctx* ctx, int32_t n_queries, const int32_t* trip
   KP_CUDA(ctx, cudaSetDevice(ctx->device));
   return kp_score_impl(ctx, n_queries, triples, mimic_rows, out, out_ld, nullptr, nullptr, 0, nullptr, nullptr,
                        nullptr, nullptr, false, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int kp_score_triples(kp_ctx* ctx, int32_t n_queries, const int32_t* triples, const float* mimic_rows, float* out,
+                                void* stream) {
+  if (!ctx) return KP_EINVAL;
+  if (n_queries < 0 || (n_queries > 0 && (!triples || !out))) KP_FAIL(ctx, KP_EINVAL, "bad score_triples arguments");
+  if (n_queries == 0) return KP_OK;
+  KP_CUDA(ctx, cudaSetDevice(ctx->device));
+  return kp_score_rows_impl(ctx, n_queries, triples, mimic_rows, out, static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int kp_filtered_rank(kp_ctx* ctx, int32_t n_queries, const int32_t* triples, const float* mimic_rows,

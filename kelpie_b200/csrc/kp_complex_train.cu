@@ -92,6 +92,7 @@ struct CxUpd {
   long long step;  // 1-based optimiser step (Adam bias correction)
   float step_size, bc2_sqrt;  // Adam: lr / (1 - beta1^step), sqrt(1 - beta2^step), evaluated in double on the host like torch
   float lr, beta1, beta2, eps, n3;
+  int reg_kind;  // KP_REG_N3: sum |f|^3 per component; KP_REG_N2: |row|_2^3 (regularizers.py:25-46)
   const float* ent;
   const float* rel;
   const int32_t *nA, *nB, *nSelf;
@@ -191,14 +192,21 @@ __global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
     for (int k = tid; k < D; k += UPD_THREADS) grad[k] += coef * qv[k];
     __syncthreads();
   }
-  // N3 (regularizers.py:37-46): w/B * sum_rows |f|^3, f = sqrt(re^2 + im^2) of lhs and rhs rows
+  // N3 (regularizers.py:37-46): w/B * sum_rows |f|^3, f = sqrt(re^2 + im^2) of lhs and rhs rows;
+  // N2 (regularizers.py:25-34): w/B * sum_rows ||f||_2^3 -- d/de = 3 ||e||_2 e per occurrence of the mimic
   const float cntM = (float)(nA + nB + p.nSelf[c]);
+  float row_norm = 0.f;
+  if (p.n3 != 0.f && p.reg_kind == KP_REG_N2) {
+    float part = 0.f;
+    for (int k = tid; k < D; k += UPD_THREADS) part = __fmaf_rn(eM[k], eM[k], part);
+    row_norm = sqrtf(block_sum(part, red));
+  }
   for (int k = tid; k < D; k += UPD_THREADS) {
     float g = grad[k];
     const float e = eM[k];
     if (p.n3 != 0.f) {
       const int kr = (k < d) ? k : k - d;
-      const float f = sqrtf(eM[kr] * eM[kr] + eM[kr + d] * eM[kr + d]);
+      const float f = (p.reg_kind == KP_REG_N2) ? row_norm : sqrtf(eM[kr] * eM[kr] + eM[kr + d] * eM[kr + d]);
       g += 3.f * p.n3 * invB * cntM * f * e;
     }
     const size_t idx = (size_t)c * D + k;
@@ -324,7 +332,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       u.step = t + 1;
       u.step_size = (float)((double)hp->lr / (1.0 - pow((double)hp->beta1, (double)(t + 1))));
       u.bc2_sqrt = (float)sqrt(1.0 - pow((double)hp->beta2, (double)(t + 1)));
-      u.lr = hp->lr; u.beta1 = hp->beta1; u.beta2 = hp->beta2; u.eps = hp->eps; u.n3 = hp->reg_weight;
+      u.lr = hp->lr; u.beta1 = hp->beta1; u.beta2 = hp->beta2; u.eps = hp->eps; u.n3 = hp->reg_weight; u.reg_kind = hp->regularizer;
       u.ent = ctx->ent; u.rel = ctx->rel;
       u.nA = pl.nA; u.nB = pl.nB; u.nSelf = pl.nSelf; u.aoff = pl.aoff; u.boff = pl.boff;
       u.a_rel = pl.a_rel; u.a_truth = pl.a_truth;

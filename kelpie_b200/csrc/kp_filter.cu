@@ -50,6 +50,7 @@ extern "C" int kp_filter_build(kp_ctx* ctx, int64_t n_facts, const int32_t* fact
     KP_FAIL(ctx, KP_EUNSUPPORTED, "kp_filter_build packs entity * R2 + relation into 31 bits (N * R2 = %llu)",
             (unsigned long long)ctx->N * (unsigned long long)ctx->R2);
   KP_CUDA(ctx, cudaSetDevice(ctx->device));
+  kp_filter_release(ctx);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int64_t n = n_facts;
   auto fresh = [&](void** p, size_t bytes) -> bool {

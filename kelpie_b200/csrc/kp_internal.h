@@ -194,6 +194,10 @@ int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic
                   float* target_score, float* best_score, int64_t* rank, int32_t* counters,
                   bool want_rank, cudaStream_t st);
 
+// out[q] = score of (s_q, p_q, o_q): query preparation + one pair score per row (Model.score)
+int kp_score_rows_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic, float* out, cudaStream_t st);
+void kp_filter_release(kp_ctx* ctx);
+
 // ---- kp_transe_train.cu / kp_complex_train.cu / kp_conve.cu -------------------------------
 int kp_transe_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st);
 int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cudaStream_t st);

@@ -281,3 +281,28 @@ int kp_score_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic
   KP_LAUNCHED(ctx, 1);
   return KP_OK;
 }
+
+int kp_score_rows_impl(kp_ctx* ctx, int Q, const int32_t* triples, const float* mimic, float* out, cudaStream_t st) {
+  const int D = ctx->D, N = (int)ctx->N;
+  const int Qpad = ((Q + 63) / 64) * 64;
+  int rc = kp_ws_reserve(ctx, WsCursor::need((size_t)Qpad * D, 4) + 2 * WsCursor::need(Q, 4));
+  if (rc != KP_OK) return rc;
+  WsCursor ws{ctx->ws, ctx->ws + ctx->ws_bytes};
+  float* qmat = ws.take<float>((size_t)Qpad * D);
+  float* self = ws.take<float>(Q);
+  int32_t* tgt_ent = ws.take<int32_t>(Q);
+  const int wpb = 8, nb = (Q + wpb - 1) / wpb;
+  int op = KP_OP_DOT, act = KP_ACT_NONE;
+  if (ctx->kind == KP_TRANSE) op = (ctx->norm == 1) ? KP_OP_L1 : KP_OP_L2;
+  if (ctx->kind == KP_CONVE) {
+    act = KP_ACT_SIGMOID;
+    if ((rc = kp_conve_features(ctx, Q, triples, 3, mimic, qmat, st)) != KP_OK) return rc;
+  } else {
+    prep_queries<<<nb, wpb * 32, 0, st>>>(ctx->kind, Q, N, (int)ctx->R2, D, ctx->ent, ctx->rel, triples, mimic, qmat);
+    KP_LAUNCHED(ctx, 1);
+  }
+  // the lane-strided accumulation of the streaming pass: 32 lanes per row instead of one sequential chain
+  target_scores<<<nb, wpb * 32, 0, st>>>(op, act, (D % 4 == 0) ? 1 : 0, Q, N, D, ctx->ent, triples, mimic, qmat, out, self, tgt_ent);
+  KP_LAUNCHED(ctx, 1);
+  return KP_OK;
+}

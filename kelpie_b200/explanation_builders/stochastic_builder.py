@@ -20,6 +20,7 @@ explanations are those of the sequential loop.  Summarisation is host-side graph
 this package: any object with `summarize(entity, triples)` / `map_rule(rule)` (e.g. the
 reference's Simulation / Bisimulation) can be passed in.
 """
+import inspect
 import itertools
 import random
 import time
@@ -60,11 +61,9 @@ class StochasticBuilder:
     # -- engine access ----------------------------------------------------------------------
     def _relevances(self, pred, rules):
         """[rule] -> ([relevance], [generator snapshot after each rule])."""
-        if hasattr(self.engine, "compute_relevances"):
-            try:
-                return self.engine.compute_relevances(pred, rules, snapshots=True)
-            except TypeError:
-                pass
+        batched = getattr(self.engine, "compute_relevances", None)
+        if batched is not None and "snapshots" in inspect.signature(batched).parameters:
+            return batched(pred, rules, snapshots=True)  # errors raised inside the engine propagate
         rels, snaps = [], []
         for r in rules:  # engines without a batch entry point (e.g. the reference's own)
             rels.append(self.engine.compute_relevance(pred, r))

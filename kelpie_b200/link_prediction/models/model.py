@@ -64,13 +64,25 @@ class Model(nn.Module):
         return self.context().all_scores(np.asarray(triples))
 
     def score(self, triples):
-        triples = np.asarray(triples)
-        sc = self.all_scores(triples)
-        idx = torch.as_tensor(triples[:, 2], device=sc.device, dtype=torch.long)
-        return sc.gather(1, idx.view(-1, 1)).view(-1).cpu().numpy()
+        """transe.py:38-46, complex.py:41-56, conve.py:68-75: the score of each triple itself -- one row of work per
+        triple (kp_score_triples), not a pass over the entity table."""
+        sc = self.context().score_triples(np.asarray(triples)).cpu().numpy()
+        return sc.reshape(-1, 1) if self.name == "ComplEx" else sc  # complex.py:56 keeps the summed dimension
 
     def forward(self, triples):
-        raise NotImplementedError("full-model training stays with the reference (SURVEY.md section 8f)")
+        """transe.py:67-75 / complex.py:59-86 / conve.py:65-66: (scores, regulariser factors) as the reference's
+        optimizers consume them.  Scores come from the device kernels; the factors are row gathers of the tables."""
+        triples = np.asarray(triples)
+        if self.name == "ConvE":
+            return self.all_scores(triples)
+        dev = self.entity_embeddings.device
+        t = torch.as_tensor(triples, device=dev, dtype=torch.long)
+        lhs, rel, rhs = self.entity_embeddings[t[:, 0]], self.relation_embeddings[t[:, 1]], self.entity_embeddings[t[:, 2]]
+        if self.name == "TransE":
+            return self.context().score_triples(triples), (lhs, rel, rhs)
+        d = self.real_dimension
+        factors = tuple(torch.sqrt(x[:, :d] ** 2 + x[:, d:] ** 2) for x in (lhs, rel, rhs))
+        return self.all_scores(triples), factors
 
     def predict_tails(self, triples):
         """model.py:42-68 / conve.py:160-184: (target scores, filtered tail ranks)."""

@@ -155,6 +155,10 @@ class MultiClassNLLOptimizer(Optimizer):
         model.cuda()
         ent = model.entity_embeddings.data.contiguous()
         rel = model.relation_embeddings.data.contiguous()
+        if hp.get("regularizer_name", "N3") != "N3" and float(hp["regularizer_weight"]) != 0:
+            # multiclass_nll_optimizer.py:46-49 also offers N2; the full-model trainer's kernels apply N3 only (the
+            # mimic post-training implements both) -- refuse rather than silently train another model
+            raise NotImplementedError("full-model ComplEx training implements the N3 regulariser only")
         fit = runtime.ComplExFit(ent, rel, hp["optimizer_name"], hp["lr"], hp["decay1"], hp["decay2"],
                                  hp["regularizer_weight"], bs)
         starts = np.arange(0, n, int(hp["batch_size"]))  # batch_start += self.batch_size (:119)

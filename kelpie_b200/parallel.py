@@ -38,21 +38,31 @@ def gather_results(local, bounds, group=None):
 
 
 class ShardedEngine:
-    """Wraps a Necessary/SufficientPostTrainingEngine: `compute_relevances` evaluates the slice of
-    rules owned by this rank and all-gathers the relevances, so every rank returns the full list.
+    """Wraps a Necessary/SufficientPostTrainingEngine for one-process-per-GPU runs: `compute_relevances` post-trains the
+    slice of rules owned by this rank and all-gathers the relevances, so every rank returns the full list.
 
-    Random numbers are drawn for EVERY candidate on every rank (cheap, host side) so that the
-    streams stay aligned with the single-process run; only the owned slice is post-trained."""
+    Every rank draws the random numbers of EVERY candidate (cheap, host side: `owned=` of the engine), so the torch /
+    numpy / CUDA generators end exactly where the single-process run leaves them, the per-candidate generator snapshots
+    the builder's early-stop rewind needs exist on every rank, and the selected explanations are those of one GPU.
+    The homologous (base) mimic of a prediction is post-trained redundantly on every rank.
+    Everything else (compute_relevance of a single candidate, select_entities_to_convert, caches) is the engine's."""
 
     def __init__(self, engine, group=None):
         self.engine, self.group = engine, group
 
-    def compute_relevances(self, pred, rules):
+    def __getattr__(self, name):  # dataset, model, hp, set_cache, select_entities_to_convert, entities_to_convert, ...
+        return getattr(self.engine, name)
+
+    def compute_relevance(self, pred, rule):
+        return self.engine.compute_relevance(pred, rule)
+
+    def compute_relevances(self, pred, rules, snapshots=False):
         world = dist.get_world_size(self.group) if dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if dist.is_initialized() else 0
         bounds = shard_bounds([len(r) + 1 for r in rules], world)
-        lo, hi = bounds[rank], bounds[rank + 1]
-        local = self.engine.compute_relevances(pred, rules[lo:hi]) if hi > lo else []
+        res = self.engine.compute_relevances(pred, rules, snapshots=snapshots, owned=(bounds[rank], bounds[rank + 1]))
+        local, snaps = res if snapshots else (res, None)
         dev = "cuda" if torch.cuda.is_available() and dist.is_initialized() and dist.get_backend(self.group) == "nccl" else "cpu"
         t = torch.tensor(local, dtype=torch.float64, device=dev).view(-1, 1)
-        return gather_results(t, bounds, self.group).view(-1).tolist()
+        rels = gather_results(t, bounds, self.group).view(-1).tolist()
+        return (rels, snaps) if snapshots else rels

@@ -83,18 +83,23 @@ class PostTrainingEngine(RelevanceEngine):
             state.append(torch.cuda.get_rng_state())
         return state
 
-    def individual_results(self, items, snapshots=None):
+    def individual_results(self, items, snapshots=None, owned=None):
         """[(pred, rule)] -> [(pt_results, base_pt_results)], RNG drawn in sequential-call order.
 
         One mimic post-training job per candidate plus one per prediction whose homologous
-        (base) mimic is not cached yet (post_training_engine.py:46-62, 78-90)."""
+        (base) mimic is not cached yet (post_training_engine.py:46-62, 78-90).
+
+        owned = (lo, hi) (candidate sharding over several GPUs, parallel.ShardedEngine): EVERY item's random numbers are
+        drawn -- so the generators end where the single-process run leaves them -- but only items lo..hi-1 are
+        post-trained; the result list then covers those items only.  Base mimics are computed on every rank."""
         model, kind = self.model, self.model.name
         ctx = context_for(model)
         N, R = self.dataset.num_entities, self.dataset.num_relations
         batch = plans.Batch(kind, N, R, self.hp, fast_rng=self.fast_rng)
+        scratch = plans.Batch(kind, N, R, self.hp, fast_rng=self.fast_rng) if owned is not None else None
         job_triple, job_filter = [], []
         pending_base, slots = {}, []
-        for pred, rule in items:
+        for index, (pred, rule) in enumerate(items):
             pred = tuple(int(x) for x in pred)
             ds = self._get_kelpie_dataset(pred[0])
             kp = ds.as_kelpie_triple(pred)
@@ -106,20 +111,28 @@ class PostTrainingEngine(RelevanceEngine):
                 job_filter.append(sorted(set(ds.to_filter.get((kp[0], kp[1]), []))))
             pt_row = self._init_row(init)  # :59
             self._apply(ds, rule)
-            j = batch.add(ds.kelpie_training_triples, pt_row)
-            job_triple.append(kp)
-            job_filter.append(sorted(set(ds.to_filter.get((kp[0], kp[1]), []))))
+            if owned is None or owned[0] <= index < owned[1]:
+                j = batch.add(ds.kelpie_training_triples, pt_row)
+                job_triple.append(kp)
+                job_filter.append(sorted(set(ds.to_filter.get((kp[0], kp[1]), []))))
+                slots.append((pred, j))
+            else:  # another rank's candidate: consume the generators exactly as its plan would
+                scratch.add(ds.kelpie_training_triples, pt_row)
             self._undo(ds)
-            slots.append((pred, j))
             if snapshots is not None:  # generator state after this candidate's draws (builder early stop)
                 snapshots.append(self._rng_snapshot())
 
+        if len(batch) == 0:  # an empty slice of a sharded batch whose base mimics are all cached
+            return []
         arrs = batch.arrays(compact=True)  # TransE: 6-byte index rows over PCIe
         hp = runtime.make_hp(kind, self.hp)
-        # ConvE dropout masks are counter-based (kp_dropout.cuh); the seed advances per batch and
-        # does not touch the host generators (the reference draws its masks on the CUDA generator)
+        # ConvE dropout masks are counter-based (kp_dropout.cuh): seeded by the user's torch seed and a per-batch counter,
+        # without touching the host generators (the reference draws its masks on the CUDA generator).  With a non-zero
+        # dropout rate (DB100K config) the masks therefore depend on how candidates were batched -- relevances are then
+        # reproducible for a given seed and batch size, not equal to a sequential run's; every rate is 0 in the DBpedia50
+        # config, where the batched and the sequential results coincide.
         self._batches = getattr(self, "_batches", 0) + 1
-        rows = ctx.post_train(hp, dropout_seed=(42 << 32) | self._batches, **arrs)
+        rows = ctx.post_train(hp, dropout_seed=((torch.initial_seed() & 0xFFFFFFFF) << 32) | self._batches, **arrs)
         flt_off = np.zeros(len(job_filter) + 1, dtype=np.int64)
         flt_off[1:] = np.cumsum([len(f) for f in job_filter])
         flt_ids = np.array([x for f in job_filter for x in f], dtype=np.int32)
@@ -160,9 +173,10 @@ class NecessaryPostTrainingEngine(PostTrainingEngine):
     def compute_relevance(self, pred, triples):
         return self.compute_relevances(pred, [triples])[0]
 
-    def compute_relevances(self, pred, rules, snapshots=False):
+    def compute_relevances(self, pred, rules, snapshots=False, owned=None):
+        """owned = (lo, hi): relevances of rules lo..hi-1 only (see individual_results); snapshots cover every rule."""
         snaps = [] if snapshots else None
-        rels = [self._relevance(pt, base) for pt, base in self.individual_results([(pred, r) for r in rules], snaps)]
+        rels = [self._relevance(pt, base) for pt, base in self.individual_results([(pred, r) for r in rules], snaps, owned)]
         return (rels, snaps) if snapshots else rels
 
 
@@ -190,15 +204,17 @@ class SufficientPostTrainingEngine(PostTrainingEngine):
     def compute_relevance(self, pred, rule):
         return self.compute_relevances(pred, [rule])[0]
 
-    def compute_relevances(self, pred, rules, snapshots=False):
-        """post_training_engine.py:178-191 for every rule: rule-major, conversion-entity-minor."""
+    def compute_relevances(self, pred, rules, snapshots=False, owned=None):
+        """post_training_engine.py:178-191 for every rule: rule-major, conversion-entity-minor.
+        owned = (lo, hi): relevances of rules lo..hi-1 only (all their conversions stay on this rank)."""
         s = pred[0]
         items = []
         for rule in rules:
             for e in self.entities_to_convert:
                 items.append((Dataset.replace_entity_in_triple(pred, s, e), Dataset.replace_entity_in_triples(rule, s, e)))
         snaps = [] if snapshots else None
-        res = [self._relevance(pt, base) for pt, base in self.individual_results(items, snaps)]
         k = len(self.entities_to_convert)
-        rels = [sum(res[i * k:(i + 1) * k]) / k for i in range(len(rules))]
+        item_range = None if owned is None else (owned[0] * k, owned[1] * k)
+        res = [self._relevance(pt, base) for pt, base in self.individual_results(items, snaps, item_range)]
+        rels = [sum(res[i * k:(i + 1) * k]) / k for i in range(len(res) // k)]
         return (rels, snaps[k - 1::k]) if snapshots else rels

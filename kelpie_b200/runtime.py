@@ -21,7 +21,7 @@ _LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libkelpie_
 EXPORTS = [
     "kp_ctx_create", "kp_ctx_destroy", "kp_last_error", "kp_abi_version", "kp_filter_upload",
     "kp_filter_build", "kp_filter_download",
-    "kp_all_scores", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
+    "kp_all_scores", "kp_score_triples", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
     "kp_debug_contract", "kp_dp_relevance",
     "kp_mt19937_words", "kp_replay_transe_corruptions", "kp_replay_numpy_shuffles",
     "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
@@ -44,6 +44,7 @@ class HP(Structure):
         ("epochs", c_int32), ("batch_size", c_int32), ("optimizer", c_int32),
         ("lr", c_float), ("beta1", c_float), ("beta2", c_float), ("eps", c_float),
         ("margin", c_float), ("reg_weight", c_float), ("label_smoothing", c_float),
+        ("regularizer", c_int32),  # ABI 3: 0 = N3, 1 = N2 (ComplEx)
     ]
 
 
@@ -88,6 +89,8 @@ def load_library():
     lib.kp_filter_download.restype = c_int
     lib.kp_all_scores.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]
     lib.kp_all_scores.restype = c_int
+    lib.kp_score_triples.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]
+    lib.kp_score_triples.restype = c_int
     lib.kp_filtered_rank.argtypes = [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                      c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]
     lib.kp_filtered_rank.restype = c_int
@@ -280,6 +283,15 @@ class Context:
                     "kp_all_scores")
         return out
 
+    def score_triples(self, triples, mimic_rows=None):
+        """[Q,3] int triples -> [Q] fp32 device tensor: the score of each triple itself (Model.score), Q rows of work."""
+        t = self.dev(triples, torch.int32).view(-1, 3)
+        Q = t.shape[0]
+        m = None if mimic_rows is None else self.dev(mimic_rows, torch.float32).view(Q, self.D)
+        out = torch.empty(Q, dtype=torch.float32, device=self.device)
+        self._check(self.lib.kp_score_triples(self.handle, Q, _ptr(t), _ptr(m), _ptr(out), self._stream()), "kp_score_triples")
+        return out
+
     def filtered_rank(self, triples, mode, mimic_rows=None, flt_off=None, flt_ids=None, counters=False):
         """Returns (target_score[Q] f32, best_score[Q] f32, rank[Q] i64[, counters[Q,4] i32]) on device."""
         t = self.dev(triples, torch.int32).view(-1, 3)
@@ -360,6 +372,7 @@ def make_hp(kind, hp):
     h.batch_size = int(hp["batch_size"])
     h.beta1, h.beta2, h.eps = 0.9, 0.999, 1e-8
     h.margin = h.reg_weight = h.label_smoothing = 0.0
+    h.regularizer = 0
     if kind == "TransE":  # pairwise_ranking_optimizer.py:44-47
         h.optimizer, h.lr = OPT_ADAM, float(hp["lr"])
         h.margin, h.reg_weight = float(hp["margin"]), float(hp["regularizer_weight"])
@@ -372,8 +385,7 @@ def make_hp(kind, hp):
         if name == "Adagrad":
             h.eps = 1e-10
         h.reg_weight = float(hp["regularizer_weight"])
-        if hp.get("regularizer_name", "N3") != "N3" and h.reg_weight != 0:
-            raise NotImplementedError("only the N3 regulariser is implemented for ComplEx post-training")
+        h.regularizer = {"N3": 0, "N2": 1}[hp.get("regularizer_name", "N3")]  # multiclass_nll_optimizer.py:46-49
     else:  # bce_optimizer.py:165 -- Adam re-created with DEFAULT lr; the config lr is ignored
         h.optimizer, h.lr = OPT_ADAM, 1e-3
         h.label_smoothing = float(hp["label_smoothing"])

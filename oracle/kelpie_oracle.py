@@ -247,6 +247,11 @@ def _n3(factors, weight):
     return sum(weight * torch.sum(torch.abs(f) ** 3) for f in factors) / factors[0].shape[0]
 
 
+def _n2(factors, weight):
+    """regularizers.py:25-34."""
+    return sum(weight * torch.sum(torch.norm(f, 2, 1) ** 3) for f in factors) / factors[0].shape[0]
+
+
 def init_mimic_row(w, init_tensor):
     """Mimic-row initialisation of the three Kelpie model classes.
 
@@ -362,7 +367,8 @@ def post_train(w, kg, mimic_row, facts, hp, log=None):
                     torch.sqrt(rr_ ** 2 + ri_ ** 2),
                     torch.sqrt(hr_ ** 2 + hi_ ** 2),
                 )
-                loss = F.cross_entropy(logits, batch[:, 2]) + _n3(factors, hp["regularizer_weight"])
+                reg = {"N3": _n3, "N2": _n2}[hp.get("regularizer_name", "N3")]  # multiclass_nll_optimizer.py:46-49
+                loss = F.cross_entropy(logits, batch[:, 2]) + reg(factors, hp["regularizer_weight"])
                 opt.zero_grad()
                 loss.backward()
                 opt.step()
@@ -626,7 +632,7 @@ def train_complex_full(ent, rel, training_triples, num_relations, hp, n_epochs=N
         opt = torch.optim.Adam([E, R], lr=hp["lr"], betas=(hp["decay1"], hp["decay2"]))
     else:
         opt = {"Adagrad": torch.optim.Adagrad, "SGD": torch.optim.SGD}[name]([E, R], lr=hp["lr"])
-    reg = {"N3": _n3, "N2": None}[hp["regularizer_name"]]
+    reg = {"N3": _n3, "N2": _n2}[hp["regularizer_name"]]
     t = np.asarray(training_triples).astype(np.int64).reshape(-1, 3)
     inv = t.copy()
     inv[:, 0], inv[:, 2] = t[:, 2], t[:, 0]

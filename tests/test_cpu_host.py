@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(runtime.EXPORTS)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.kp_abi_version() == 2
+    assert lib.kp_abi_version() == 3
 
 
 def test_no_cpu_fallback():
@@ -45,7 +45,7 @@ def test_no_cpu_fallback():
 
 def test_struct_layouts_match_header():
     from kelpie_b200 import runtime
-    assert ctypes.sizeof(runtime.HP) == 40
+    assert ctypes.sizeof(runtime.HP) == 44  # ABI 3: + regularizer
     assert ctypes.sizeof(runtime.PTBatch) == 96 + 4 * 8  # ABI 2: the compact TransE tables
     assert ctypes.sizeof(runtime.ConvEWeights) == 7 * 8 + 5 * 4 + 4
 
@@ -157,14 +157,29 @@ import torch, torch.distributed as dist
 from kelpie_b200.parallel import ShardedEngine
 
 class FakeEngine:  # MockEngine pattern of the reference's builder tests (test_stochastic_builder.py:7-11)
-    def compute_relevances(self, pred, rules):
-        return [float(sum(t[2] for t in r)) + 0.5 for r in rules]
+    """Draws one random number per rule -- for EVERY rule, owned or not, as the real engines do -- so the test also
+    checks that the generators of all ranks end where the single-process run leaves them."""
+    def compute_relevances(self, pred, rules, snapshots=False, owned=None):
+        lo, hi = owned if owned is not None else (0, len(rules))
+        noise = [float(torch.rand(1)) for _ in rules]
+        rels = [float(sum(t[2] for t in r)) + 0.5 + noise[i] for i, r in enumerate(rules)][lo:hi]
+        return (rels, [torch.get_rng_state() for _ in rules]) if snapshots else rels
+    def compute_relevance(self, pred, rule):
+        return self.compute_relevances(pred, [rule])[0]
 
 dist.init_process_group("gloo")
 rules = [[(1, 0, i)] * (1 + i % 3) for i in range(11)]
-got = ShardedEngine(FakeEngine()).compute_relevances((1, 0, 2), rules)
+torch.manual_seed(5)
+eng = ShardedEngine(FakeEngine())
+got = eng.compute_relevances((1, 0, 2), rules)
+tail = float(torch.rand(1))
+got2, snaps = eng.compute_relevances((1, 0, 2), rules, snapshots=True)   # the builder's calling convention
+assert len(got2) == len(rules) == len(snaps)
+assert isinstance(eng.compute_relevance((1, 0, 2), rules[0]), float)
+torch.manual_seed(5)
 want = FakeEngine().compute_relevances((1, 0, 2), rules)
 assert got == want, (got, want)
+assert tail == float(torch.rand(1))   # same generator position as the single-process run
 dist.barrier()
 dist.destroy_process_group()
 print("ok", dist.is_initialized())

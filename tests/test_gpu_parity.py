@@ -146,3 +146,107 @@ def test_evaluator_metrics_match_golden_ranks(kind):
     assert got["mr"] == pytest.approx(float(np.mean(ranks)))
     assert got["h1"] == pytest.approx(float(np.mean(ranks <= 1)))
     assert got["h10"] == pytest.approx(float(np.mean(ranks <= 10)))
+
+
+def test_transe_mimic_row_drawn_on_the_cuda_generator():
+    """The DEFAULT rng_device ("cuda"): KelpieTransE overwrites its mimic row with xavier_normal_ on the row's device
+    (transe.py:93-95: Parameter(init_tensor.cuda()) then xavier_normal_), i.e. on the CUDA generator when the reference
+    runs on a GPU.  The engine's draw must be torch's own: same values, same generator state afterwards, two draws per
+    compute_relevance (base model, then post-trained model) -- and it must end up in the post-training unchanged."""
+    from torch.nn.init import xavier_normal_
+    from kelpie_b200.relevance_engines import NecessaryPostTrainingEngine
+    z, meta, kg, w, order = load("TransE")
+    ds = _dataset(z)
+    m = _model("TransE", z, meta, ds)
+    eng = NecessaryPostTrainingEngine(m, ds, meta["hp"])
+    assert eng.rng_device == "cuda"
+    D = m.dimension
+    torch.manual_seed(321)  # seeds the CPU and the CUDA generators
+    init = torch.rand(1, D)
+    got = [eng._init_row(init), eng._init_row(init)]
+    tail = torch.rand(4, device="cuda")
+    torch.manual_seed(321)
+    init_ref = torch.rand(1, D)
+    want = []
+    for _ in range(2):
+        p = torch.nn.Parameter(init_ref.cuda(), requires_grad=True)
+        with torch.no_grad():
+            xavier_normal_(p)
+        want.append(p.detach())
+    assert torch.equal(torch.rand(4, device="cuda"), tail)  # the CUDA generator advanced exactly as the reference's would
+    for a, b in zip(got, want):
+        assert a.is_cuda and torch.equal(a.view(-1), b.view(-1))
+    # end to end with the default device: the rows the batch is post-trained from are those draws
+    case = meta["cases"][0]
+    pred, rules = tuple(case["pred"]), [[tuple(t) for t in r] for r in case["rules"]][:2]
+    torch.manual_seed(77)
+    eng.set_cache()
+    rels = eng.compute_relevances(pred, rules)
+    torch.manual_seed(77)
+    eng2 = NecessaryPostTrainingEngine(m, ds, meta["hp"])
+    rels2 = [eng2.compute_relevance(pred, r) for r in rules]  # the reference's sequential calls
+    np.testing.assert_allclose(rels, rels2, rtol=RTOL, atol=RTOL)
+    assert all(np.isfinite(rels))
+
+
+def test_complex_n2_regulariser_golden():
+    """kp_hp.regularizer = N2 (regularizers.py:25-34): post-trained rows, ranks and relevances vs the unmodified reference."""
+    import json
+    import os
+    from tests.golden_util import GOLDEN
+    from kelpie_b200.relevance_engines import NecessaryPostTrainingEngine
+    z, meta, kg, w, order = load("ComplEx")
+    g = np.load(os.path.join(GOLDEN, "complex_n2_small.npz"))
+    gm = json.loads(bytes(g["meta"]).decode())
+    ds = _dataset(z)
+    for e, facts in order.items():
+        ds.entity_to_training_triples[e] = [tuple(t) for t in facts]
+    m = _model("ComplEx", z, meta, ds)
+    eng = NecessaryPostTrainingEngine(m, ds, gm["hp"])
+    pred, rules = tuple(gm["pred"]), [[tuple(t) for t in r] for r in gm["rules"]]
+    seed_all(gm["seed"])
+    eng.set_cache()
+    got_rows, got_res = [], []
+    for r in rules:
+        n_before = len(eng.base_pt_results)
+        pt, base = eng.individual_results([(pred, r)])[0]
+        rows = eng.last_rows.cpu().numpy()
+        if len(eng.base_pt_results) > n_before:
+            got_rows.append(rows[0]); got_res.append(base)
+        got_rows.append(rows[-1]); got_res.append(pt)
+    ref = trace_of(g, "n2_")
+    assert len(got_rows) == len(ref)
+    for row, res, (r_init, r_final, r_res) in zip(got_rows, got_res, ref):
+        _close(row, r_final.reshape(-1))
+        assert int(res["target_rank"]) == int(r_res[1])
+        assert abs(res["target_score"] - r_res[0]) <= RTOL * max(1.0, abs(r_res[0]))
+    seed_all(gm["seed"])
+    eng.set_cache()
+    np.testing.assert_allclose(eng.compute_relevances(pred, rules), g["n2_relevance"], rtol=RTOL, atol=RTOL)
+
+
+@pytest.mark.parametrize("kind", ["TransE", "ComplEx", "ConvE"])
+def test_model_score_and_forward(kind):
+    """Model.score (one row of work per triple, kp_score_triples) and Model.forward against the golden all_scores
+    of the unmodified reference (transe.py:38-46,67-75, complex.py:41-86, conve.py:65-75)."""
+    z, meta, kg, w, order = load(kind)
+    ds = _dataset(z)
+    m = _model(kind, z, meta, ds)
+    q = z["all_scores_q"]
+    want = z["all_scores"][np.arange(len(q)), q[:, 2]]
+    got = np.asarray(m.score(q)).reshape(-1)
+    _close(got, want)
+    out = m.forward(q)
+    if kind == "ConvE":
+        _close(out.cpu().numpy(), z["all_scores"])
+    else:
+        sc, factors = out
+        assert len(factors) == 3 and all(f.shape[0] == len(q) for f in factors)
+        if kind == "TransE":
+            _close(sc.cpu().numpy(), want)
+            np.testing.assert_array_equal(factors[0].cpu().numpy(), z["w_ent"][q[:, 0]])
+        else:
+            _close(sc.cpu().numpy(), z["all_scores"])
+            d = z["w_ent"].shape[1] // 2
+            l = z["w_ent"][q[:, 0]]
+            _close(factors[0].cpu().numpy(), np.sqrt(l[:, :d] ** 2 + l[:, d:] ** 2))

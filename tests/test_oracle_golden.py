@@ -59,3 +59,20 @@ def test_convertible_entities_match_reference(kind):
     z, meta, kg, w, _ = load(kind)
     got = sorted(ko.convertible_entities(w, kg, tuple(meta["convertible_pred"]), 200))
     np.testing.assert_array_equal(got, z["convertible"])
+
+
+def test_n2_regulariser_matches_reference():
+    """regularizers.py:25-34 (N2, weight 0.05) through the unmodified reference vs the oracle: tests/golden/make_golden_n2.py."""
+    import json
+    import os
+    from tests.golden_util import GOLDEN
+    z, meta, kg, w, order = load("ComplEx")
+    g = np.load(os.path.join(GOLDEN, "complex_n2_small.npz"))
+    gm = json.loads(bytes(g["meta"]).decode())
+    eng = ko.Engine(w, kg, gm["hp"], mode="necessary", fact_order=order)
+    seed_all(gm["seed"])
+    rels = [eng.compute_relevance(tuple(gm["pred"]), [tuple(t) for t in r]) for r in gm["rules"]]
+    _check_trace(eng, g, "n2_")
+    np.testing.assert_allclose(rels, g["n2_relevance"], rtol=1e-5, atol=1e-5)
+    # the regulariser did change the result: the N3 run of the same case gives other rows
+    assert np.abs(g["n2_1_final"] - z["nec0_1_final"]).max() > 1e-5

@@ -9,11 +9,12 @@ wl = sys.argv[1] if len(sys.argv) > 1 else "transe_dbpedia50"
 variant = 0
 cfg = bench.PRESETS[wl]
 
-ent, rel, conve, D = bench.make_tables(cfg, torch.device("cuda:0"))
-ctx = runtime.Context(cfg["kind"], ent, rel, norm=2, device=0)
+ent, rel, conve, D = bench.make_tables(cfg)
+ctx = runtime.Context(cfg["kind"], ent.cuda(), rel.cuda(), norm=2, device=0)
 
 hp = runtime.make_hp(cfg["kind"], cfg["hp"])
-arrs, triples, flt_off, flt_ids, jobs, filters = bench.make_batch(cfg, D, cfg["C"], 1000)
+batch = bench.make_jobs(cfg, D, cfg["C"])
+arrs, triples, flt_off, flt_ids = bench.build_arrays(cfg, batch, list(range(len(batch["jobs"]))))
 dt = dict(init_rows=torch.float32, row_off=torch.int64, rows_per_epoch=torch.int32, pos=torch.int32, neg=torch.int32,
           fact_off=torch.int64, facts=torch.int32, pos_idx=torch.uint16, neg_code=torch.int32)
 dev = {k: ctx.dev(v, dt[k]) for k, v in arrs.items() if k != "static_epochs" and v is not None}
