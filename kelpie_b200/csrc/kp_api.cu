@@ -123,7 +123,9 @@ extern "C" int kp_stat(kp_ctx* ctx, const char* name, double* out) {
     if (!strncmp(name, "n_", 2) && !strcmp(name + 2, cats[i])) { *out = (double)ctx->t_n[i]; return KP_OK; }
   }
   if (!strcmp(name, "rank_rechecks")) {
-    *out = (double)ctx->rank_rechecks;
+    unsigned long long v = 0;
+    if (ctx->rank_recheck_total) KP_CUDA(ctx, cudaMemcpy(&v, ctx->rank_recheck_total, sizeof(v), cudaMemcpyDeviceToHost));
+    *out = (double)v;
     return KP_OK;
   }
   if (!strncmp(name, "umma_prof_", 10) && ctx->umma_prof) {  // slot / own / for / total (MMA-thread cycles, summed over pairs)

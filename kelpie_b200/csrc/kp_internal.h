@@ -69,7 +69,7 @@ struct kp_ctx {
   std::map<TmapKey, CUtensorMap> tmaps;
 
   int64_t launches = 0;
-  int64_t rank_rechecks = 0;  // pairs the tensor-core rank pass handed to the exact re-check so far
+  unsigned long long* rank_recheck_total = nullptr;  // device counter: pairs the tensor-core rank pass handed to the exact re-check
   int64_t force_simt = 0;
   int64_t skinny_fc = 1;      // ConvE Linear forward of < 128 rows on the skinny kernel (else the tiled CUDA-core GEMM)
   int64_t cx_merge = 1;       // ComplEx: strips merged per row by cx_merge_strips before the per-candidate update

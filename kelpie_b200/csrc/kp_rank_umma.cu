@@ -65,6 +65,12 @@ struct RK {
   int2* pairs;             // re-check list (query, entity)
   unsigned long long* n_pairs;
   unsigned long long cap_pairs;
+  // exact re-evaluation in place when the list is full (degenerate scores): no host round trip decides anything
+  const float* qmat;       // [Qn, D] fp32 queries
+  const float* ent;        // [N, D] fp32 table
+  const float* target;     // [Qn]
+  uint32_t* best_act;      // [Qn] kp_ord of the best re-checked ACTIVATED score
+  int act;
 };
 
 __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
@@ -75,6 +81,52 @@ __device__ __forceinline__ uint64_t udesc(uint32_t saddr, uint32_t lbo_bytes, ui
   d |= (uint64_t)1 << 46;
   d |= (uint64_t)2 << 61;
   return d;
+}
+
+__device__ __forceinline__ float act_apply(int act, float x) {
+  if (act == KP_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
+  if (act == ACT_NEGSQRT) return -sqrtf(-x);
+  return x;
+}
+
+// Exact score of (query q, entity j) with the arithmetic of the exact pass (kp_pass.cu: one sequential fp32 FMA chain),
+// folded into the counters.
+__device__ __forceinline__ void recheck_pair(int q, int j, int D, int act, const float* __restrict__ qmat, const float* __restrict__ ent,
+                                             const float* __restrict__ target, const int32_t* __restrict__ tgt_ent,
+                                             int32_t* __restrict__ cnt, uint32_t* __restrict__ best_act) {
+  const float4* a = reinterpret_cast<const float4*>(qmat + (size_t)q * D);
+  const float4* b = reinterpret_cast<const float4*>(ent + (size_t)j * D);
+  float acc = 0.f;
+  if (act == ACT_NEGSQRT) {  // kp_pass.cu accum<KP_OP_L2>
+    for (int k = 0; k < D / 4; ++k) {
+      const float4 x = a[k], y = b[k];
+      float d = __fsub_rn(x.x, y.x);
+      acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(x.y, y.y);
+      acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(x.z, y.z);
+      acc = __fmaf_rn(d, d, acc);
+      d = __fsub_rn(x.w, y.w);
+      acc = __fmaf_rn(d, d, acc);
+    }
+    acc = -acc;
+  } else {
+    for (int k = 0; k < D / 4; ++k) {
+      const float4 x = a[k], y = b[k];
+      acc = __fmaf_rn(x.x, y.x, acc);
+      acc = __fmaf_rn(x.y, y.y, acc);
+      acc = __fmaf_rn(x.z, y.z, acc);
+      acc = __fmaf_rn(x.w, y.w, acc);
+    }
+  }
+  const float sc = act_apply(act, acc);  // L2: minus the distance, compared with minus the target's
+  const float t = (act == ACT_NEGSQRT) ? -target[q] : target[q];
+  if (sc > t) atomicAdd(&cnt[q * 4 + 0], 1);
+  if (sc == t) {
+    atomicAdd(&cnt[q * 4 + 1], 1);
+    if (j < tgt_ent[q]) atomicAdd(&cnt[q * 4 + 2], 1);
+  }
+  atomicMax(&best_act[q], kp_ord(sc));
 }
 
 template <bool L2>
@@ -256,7 +308,10 @@ rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_cons
           const int c = __ffs(unsure) - 1;
           unsure &= unsure - 1;
           const unsigned long long at = atomicAdd(p.n_pairs, 1ull);
-          if (at < p.cap_pairs) p.pairs[at] = make_int2(q, j0 + c0 + c);
+          if (at < p.cap_pairs)
+            p.pairs[at] = make_int2(q, j0 + c0 + c);
+          else  // list full (degenerate scores): evaluate here, slowly but exactly
+            recheck_pair(q, j0 + c0 + c, p.D, p.act, p.qmat, p.ent, p.target, p.tgt_ent, p.cnt, p.best_act);
         }
       }
       ptx::tc_fence_before();
@@ -273,11 +328,6 @@ rank_umma_kernel(const __grid_constant__ CUtensorMap eh64_map, const __grid_cons
   if (warp == 1) ptx::tmem_dealloc2(tm, 256);
 }
 
-__device__ __forceinline__ float act_apply(int act, float x) {
-  if (act == KP_ACT_SIGMOID) return 1.f / (1.f + expf(-x));
-  if (act == ACT_NEGSQRT) return -sqrtf(-x);
-  return x;
-}
 
 // Per query: |q|_2 and the pre-activation thresholds.  target[q] is the (activated) target score the
 // exact pass would compare with; NaN (invalid triple) -> nothing is ever better or tied.
@@ -336,46 +386,17 @@ __global__ void rank_prepare(int Q, int Qpad, int D, int act, const float* __res
 }
 
 // Exact arithmetic of kp_pass.cu for the pairs the tensor-core pass could not decide: one thread per pair.
-__global__ void rank_recheck(unsigned long long n, const int2* __restrict__ pairs, int D, int act, const float* __restrict__ qmat,
+// The undecided pairs of the tensor-core pass, re-evaluated exactly.  The list length is read on the DEVICE (fixed
+// grid-stride launch): the host never waits for the pass, so a caller can queue step k+1 behind step k.
+__global__ void rank_recheck(const unsigned long long* __restrict__ n_ptr, unsigned long long cap, unsigned long long* __restrict__ total,
+                             const int2* __restrict__ pairs, int D, int act, const float* __restrict__ qmat,
                              const float* __restrict__ ent, const float* __restrict__ target, const int32_t* __restrict__ tgt_ent,
                              int32_t* __restrict__ cnt, uint32_t* __restrict__ best_act) {
+  const unsigned long long all = *n_ptr, n = all < cap ? all : cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0 && total) atomicAdd(total, all);
   for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x; i < n;
-       i += (unsigned long long)gridDim.x * blockDim.x) {
-    const int2 pr = pairs[i];
-    const float4* a = reinterpret_cast<const float4*>(qmat + (size_t)pr.x * D);
-    const float4* b = reinterpret_cast<const float4*>(ent + (size_t)pr.y * D);
-    float acc = 0.f;
-    if (act == ACT_NEGSQRT) {  // kp_pass.cu accum<KP_OP_L2>
-      for (int k = 0; k < D / 4; ++k) {
-        const float4 x = a[k], y = b[k];
-        float d = __fsub_rn(x.x, y.x);
-        acc = __fmaf_rn(d, d, acc);
-        d = __fsub_rn(x.y, y.y);
-        acc = __fmaf_rn(d, d, acc);
-        d = __fsub_rn(x.z, y.z);
-        acc = __fmaf_rn(d, d, acc);
-        d = __fsub_rn(x.w, y.w);
-        acc = __fmaf_rn(d, d, acc);
-      }
-      acc = -acc;
-    } else {
-      for (int k = 0; k < D / 4; ++k) {
-        const float4 x = a[k], y = b[k];
-        acc = __fmaf_rn(x.x, y.x, acc);
-        acc = __fmaf_rn(x.y, y.y, acc);
-        acc = __fmaf_rn(x.z, y.z, acc);
-        acc = __fmaf_rn(x.w, y.w, acc);
-      }
-    }
-    const float sc = act_apply(act, acc);  // L2: minus the distance, compared with minus the target's
-    const float t = (act == ACT_NEGSQRT) ? -target[pr.x] : target[pr.x];
-    if (sc > t) atomicAdd(&cnt[pr.x * 4 + 0], 1);
-    if (sc == t) {
-      atomicAdd(&cnt[pr.x * 4 + 1], 1);
-      if (pr.y < tgt_ent[pr.x]) atomicAdd(&cnt[pr.x * 4 + 2], 1);
-    }
-    atomicMax(&best_act[pr.x], kp_ord(sc));
-  }
+       i += (unsigned long long)gridDim.x * blockDim.x)
+    recheck_pair(pairs[i].x, pairs[i].y, D, act, qmat, ent, target, tgt_ent, cnt, best_act);
 }
 
 // best[q]: pre-activation maximum from the tensor-core pass -> activated, merged with the re-checked exact scores
@@ -455,6 +476,11 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   p.pairs = pairs;
   p.n_pairs = n_pairs;
   p.cap_pairs = cap;
+  p.qmat = a.qmat;
+  p.ent = ctx->ent;
+  p.target = a.target;
+  p.best_act = best_act;
+  p.act = act;
   static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   if (!configured) {
     KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
@@ -469,22 +495,17 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
       rank_umma_kernel<false><<<dim3(n_qt, n_strips, 1), RT, R_SMEM, st>>>(ctx->um.eh64_map, ctx->um.el64_map, qh_map, ql_map, p);
   }
   KP_LAUNCHED(ctx, 1);
-  // the list length decides the re-check grid (and whether the list overflowed): one small synchronous read
-  unsigned long long n = 0;
-  KP_CUDA(ctx, cudaMemcpyAsync(&n, n_pairs, sizeof(n), cudaMemcpyDeviceToHost, st));
-  KP_CUDA(ctx, cudaStreamSynchronize(st));
-  ctx->rank_rechecks += (int64_t)n;
-  if (n > cap) {
-    // too many undecided pairs (degenerate scores, e.g. a saturated sigmoid): the exact pass redoes the batch
-    KP_CUDA(ctx, cudaMemsetAsync(a.cnt, 0, (size_t)Q * 16, st));
-    return kp_pass_launch(ctx, a, st);
+  // the undecided pairs (0.1 - 0.2 %) are re-evaluated by a fixed grid that reads the list length on the device
+  if (!ctx->rank_recheck_total) {
+    void* d = nullptr;
+    if (cudaMalloc(&d, sizeof(unsigned long long)) != cudaSuccess) KP_FAIL(ctx, KP_ENOMEM, "re-check counter");
+    ctx->owned.push_back(d);
+    KP_CUDA(ctx, cudaMemsetAsync(d, 0, sizeof(unsigned long long), st));
+    ctx->rank_recheck_total = static_cast<unsigned long long*>(d);
   }
-  if (n > 0) {
-    unsigned blocks = (unsigned)((n + 255) / 256);
-    if (blocks > (unsigned)ctx->sm_count * 16) blocks = (unsigned)ctx->sm_count * 16;
-    rank_recheck<<<blocks, 256, 0, st>>>(n, pairs, D, act, a.qmat, ctx->ent, a.target, a.tgt_ent, a.cnt, best_act);
-    KP_LAUNCHED(ctx, 1);
-  }
+  rank_recheck<<<(unsigned)ctx->sm_count * 8, 256, 0, st>>>(n_pairs, cap, ctx->rank_recheck_total, pairs, D, act, a.qmat, ctx->ent,
+                                                            a.target, a.tgt_ent, a.cnt, best_act);
+  KP_LAUNCHED(ctx, 1);
   rank_best_finish<<<(Q + 255) / 256, 256, 0, st>>>(Q, act, best_pre, best_act, a.best);
   KP_LAUNCHED(ctx, 1);
   return KP_OK;

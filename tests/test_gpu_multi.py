@@ -1,8 +1,9 @@
 """Multi-GPU product path on real NCCL: one process per GPU, every rank holds the full tables,
 `parallel.ShardedEngine` post-trains a cost-balanced slice of the candidates on its GPU and all-gathers the relevances.
-Asserted: the gathered list equals the single-GPU list of the same engine BIT FOR BIT, every rank's generators end where
-the single-process run leaves them, and the StochasticBuilder driven through the sharded engine selects the same
-explanation with the same number of evaluated candidates.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped elsewhere."""
+Asserted: the gathered list equals the single-GPU list of the same engine (TransE: bit for bit; ComplEx / ConvE: to fp32
+rounding, see the worker), every rank's generators end bit for bit where the single-process run leaves them, and the
+StochasticBuilder driven through the sharded engine selects the same explanations with the same number of evaluated
+candidates.  Needs >= 2 GPUs (`gpurun --gpus 2`); skipped elsewhere."""
 import os
 import socket
 import subprocess
@@ -33,6 +34,9 @@ ds = _dataset(z)
 for e, facts in order.items():
     ds.entity_to_training_triples[e] = [tuple(t) for t in facts]
 m = _model(kind, z, meta, ds)
+# one scoring kernel whatever the number of queries a rank ends up with (by default <= 8 queries take the streaming
+# kernel, whose lane-strided sums differ from the tile kernel's sequential chain in the last bit)
+m.context().set_option("force_tile", 1)
 for case in meta["cases"]:
     cls = NecessaryPostTrainingEngine if case["mode"] == "necessary" else SufficientPostTrainingEngine
     pred = tuple(case["pred"])
@@ -48,7 +52,16 @@ for case in meta["cases"]:
         e = ShardedEngine(eng) if sharded else eng
         rels = e.compute_relevances(pred, rules)
         out[sharded] = (rels, float(torch.rand(1)), float(np.random.random()), float(torch.rand(1, device="cuda")))
-    assert out[True] == out[False], (kind, case["tag"], dist.get_rank(), out)   # bit for bit, generators included
+    if out[True] != out[False]:
+        print("last-bit differences", kind, case["tag"], "rank", dist.get_rank(), "\n sharded", out[True], "\n single ", out[False], flush=True)
+    assert out[True][1:] == out[False][1:]   # the torch / numpy / CUDA generators: bit for bit
+    # relevances: TransE bit for bit; ComplEx / ConvE to fp32 rounding -- the fused pass cuts the entity range into strips
+    # according to how many rows the launch holds, so a slice sums the same terms in another order (integer rank deltas
+    # are exact either way: a difference there would be >= 1 / base rank)
+    if kind == "TransE":
+        assert out[True][0] == out[False][0]
+    else:
+        np.testing.assert_allclose(out[True][0], out[False][0], rtol=2e-6, atol=1e-7)
 # the explanation builder through the sharded engine: same explanation, same number of relevances
 case = meta["cases"][0]
 pred = tuple(case["pred"])
@@ -61,7 +74,9 @@ for sharded in (False, True):
     b = StochasticBuilder(10.0 ** 9, ShardedEngine(eng) if sharded else eng, batch_size=4)
     r = b.build_explanations(pred, facts, k=5)
     res[sharded] = (r["rule_to_relevance"], r["#relevances"])
-assert res[True] == res[False], (kind, res)
+assert res[True][1] == res[False][1], (kind, res)                                # same number of evaluated candidates
+assert [r for r, _ in res[True][0]] == [r for r, _ in res[False][0]], (kind, res)  # same explanations, same order
+np.testing.assert_allclose([v for _, v in res[True][0]], [v for _, v in res[False][0]], rtol=2e-6, atol=1e-7)
 dist.barrier()
 dist.destroy_process_group()
 print("ok")

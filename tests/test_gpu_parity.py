@@ -179,10 +179,10 @@ def test_transe_mimic_row_drawn_on_the_cuda_generator():
     # end to end with the default device: the rows the batch is post-trained from are those draws
     case = meta["cases"][0]
     pred, rules = tuple(case["pred"]), [[tuple(t) for t in r] for r in case["rules"]][:2]
-    torch.manual_seed(77)
+    seed_all(77)  # torch (CPU + CUDA) and numpy: the corruptions come from torch.randint, the shuffles from np.random
     eng.set_cache()
     rels = eng.compute_relevances(pred, rules)
-    torch.manual_seed(77)
+    seed_all(77)
     eng2 = NecessaryPostTrainingEngine(m, ds, meta["hp"])
     rels2 = [eng2.compute_relevance(pred, r) for r in rules]  # the reference's sequential calls
     np.testing.assert_allclose(rels, rels2, rtol=RTOL, atol=RTOL)
@@ -244,9 +244,9 @@ def test_model_score_and_forward(kind):
         assert len(factors) == 3 and all(f.shape[0] == len(q) for f in factors)
         if kind == "TransE":
             _close(sc.cpu().numpy(), want)
-            np.testing.assert_array_equal(factors[0].cpu().numpy(), z["w_ent"][q[:, 0]])
+            np.testing.assert_array_equal(factors[0].detach().cpu().numpy(), z["w_ent"][q[:, 0]])
         else:
             _close(sc.cpu().numpy(), z["all_scores"])
             d = z["w_ent"].shape[1] // 2
             l = z["w_ent"][q[:, 0]]
-            _close(factors[0].cpu().numpy(), np.sqrt(l[:, :d] ** 2 + l[:, d:] ** 2))
+            _close(factors[0].detach().cpu().numpy(), np.sqrt(l[:, :d] ** 2 + l[:, d:] ** 2))
