@@ -565,8 +565,10 @@ def main():
     issue_copy(0)
     warm_done, step_s = 0, None
     for i in range(args.warmup):
-        # at least 3 warm-up steps; beyond that only while warm-up + 3 timed steps still fit the budget
-        if agree(i >= 3 and step_s is not None and elapsed() + (args.warmup - i + 3) * step_s > budget):
+        # at least 3 warm-up steps (clocks and caches settle within the first: a step is >= tens of ms of dense work);
+        # beyond that only while the remaining warm-up AND every requested timed step still fit the budget
+        if agree(i >= 3 and step_s is not None and elapsed() + (args.warmup - i + args.steps) * step_s * 1.02 + 15.0 > budget):
+            log(f"[rank {rank}] wall budget {budget:.0f} s: {i} warm-up steps instead of {args.warmup} so that the timed steps fit")
             break
         t = time.time()
         step()
