@@ -15,7 +15,13 @@
  *   - all work is enqueued on the caller's stream (cudaStream_t passed as void*), the
  *     calls are asynchronous unless stated otherwise;
  *   - entity ids are int32 on the device (N < 2^31); ranks are int64 like the reference's;
- *   - there is NO CPU fallback: without a CUDA device every call fails with KP_ECUDA.
+ *   - there is NO CPU fallback: without a CUDA device every call fails with KP_ECUDA;
+ *   - ONE stream per context at a time: a context owns a single grow-only workspace arena that every call carves its
+ *     scratch from, so calls on different streams (or host threads) must be serialised by the caller; use one context
+ *     per GPU (several GPUs: one process / one context each, kelpie_b200.parallel).  kp_last_error(NULL) (the message
+ *     of a failed kp_ctx_create) is thread-local;
+ *   - ids are trusted: the scoring / ranking calls answer NaN for a query id outside [0, N] / [0, R2), the training
+ *     kernels do not range-check the ids of a batch -- they come from the dataset the context was built from.
  */
 #ifndef KELPIE_B200_H
 #define KELPIE_B200_H

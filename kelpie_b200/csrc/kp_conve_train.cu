@@ -318,16 +318,12 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   const float tb = ls != 0.f ? 1.f / (float)(ctx->N + 1) : 0.f;
   const int cb = (C + 127) / 128;
   int64_t GA = 0, GB = 0;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
   const int Hc = ctx->cv.H, Fc = ctx->cv.n_filters;
   const size_t back_smem = ((size_t)Fc * ((38 * (Hc - 2)) | 1) + 10 * Fc) * sizeof(float);
   if (back_smem > 200 * 1024) KP_FAIL(ctx, KP_EUNSUPPORTED, "ConvE hidden size %d too large", hidden);
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    KP_CUDA(ctx, cudaFuncSetAttribute(cv_backward_generic, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, (cv_backward<10>), 200 * 1024);
+  KP_SMEM_ONCE(ctx, (cv_backward<4>), 200 * 1024);
+  KP_SMEM_ONCE(ctx, cv_backward_generic, 200 * 1024);
   const bool static_plan = spe_max <= 1;
   for (long long t = 0; t < T; ++t) {
     if (t == 0 || !static_plan) {

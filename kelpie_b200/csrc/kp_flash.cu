@@ -220,12 +220,7 @@ int kp_flash_simt(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   const int ov = (p.D + 63) / 64;
 #define KP_FLASH_CASE(V)                                                                                           \
   {                                                                                                                \
-    static bool configured_dev[64] = {};                                                                           \
-    bool& configured = configured_dev[ctx->device & 63]; /* the attribute is per device */                         \
-    if (!configured) {                                                                                             \
-      KP_CUDA(ctx, cudaFuncSetAttribute(flash_simt_kernel<V>, cudaFuncAttributeMaxDynamicSharedMemorySize, 208 * 1024)); \
-      configured = true;                                                                                           \
-    }                                                                                                              \
+    KP_SMEM_ONCE(ctx, (flash_simt_kernel<V>), 208 * 1024);                                                         \
     KpTimer timer(ctx, kp_ctx::T_FLASH, st);                                                                        \
     flash_simt_kernel<V><<<grid, FTHREADS, smem, st>>>(p);                                                         \
   }

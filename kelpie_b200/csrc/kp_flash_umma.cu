@@ -467,11 +467,7 @@ int kp_flash_umma(kp_ctx* ctx, const float* qmat, int G, int mode, float* part_m
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U_SMEM));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, flash_umma_kernel, U_SMEM);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(u.n_strips, u.n_qt, u.cc);
   cfg.blockDim = dim3(UT);

@@ -290,11 +290,7 @@ int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   // two dim chunks = two clusters per (query tiles, strip) whose lazy reference maxima must agree: they have to
   // visit the tiles in the same order, so the rotating start is only used by the single-chunk pass
   p.cursor = (ctx->umma_rotate && n_chunks == 1) ? ctx->umma_cursor : nullptr;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U2_SMEM));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, flash_umma2_kernel, U2_SMEM);
   if (n_qt % 2 != 0) KP_FAIL(ctx, KP_EINVAL, "pair kernel needs an even number of query tiles (%d)", n_qt);
   {
     int max_clusters = -1;

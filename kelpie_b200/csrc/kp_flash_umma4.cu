@@ -466,11 +466,7 @@ int kp_flash_umma4_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   p.part_O = part_O;
   p.prof = ctx->umma_prof;
   p.cursor = ctx->umma_rotate ? ctx->umma_cursor : nullptr;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma4_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)U4_SMEM));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, flash_umma4_kernel, U4_SMEM);
   if (n_qt % 2 != 0) KP_FAIL(ctx, KP_EINVAL, "cluster-4 kernel needs an even number of query tiles (%d)", n_qt);
   {
     KpTimer timer(ctx, kp_ctx::T_FLASH, st);

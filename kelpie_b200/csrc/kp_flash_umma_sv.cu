@@ -513,7 +513,7 @@ int kp_flash_umma_sv_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtens
   if (n_qt % 2 != 0 || tps % 2 != 0)
     KP_FAIL(ctx, KP_EINVAL, "S/V kernel needs an even number of query tiles (%d) and of tiles per strip (%d)", n_qt, tps);
   if (ngroup < 1 || ngroup > 2) KP_FAIL(ctx, KP_EINVAL, "S/V kernel holds at most 512 output dims (%d groups)", ngroup);
-  KP_CUDA(ctx, cudaFuncSetAttribute(flash_umma_sv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SV_SMEM));
+  KP_SMEM_ONCE(ctx, flash_umma_sv_kernel, SV_SMEM);
   {
     KpTimer timer(ctx, kp_ctx::T_FLASH, st);
     flash_umma_sv_kernel<<<dim3(2 * n_qt, n_strips, 1), UT, SV_SMEM, st>>>(ctx->um.eh_map, ctx->um.el_map, ctx->um.eh64_map,

@@ -349,12 +349,8 @@ int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, in
   }
   p.C = C;
   p.ldc = ldc;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, (gemm_umma_kernel<false>), G_SMEM);
+  KP_SMEM_ONCE(ctx, (gemm_umma_kernel<true>), G_SMEM);
   {
     KpTimer timer(ctx, kp_ctx::T_CONV, st);
     if (tf32) gemm_umma_kernel<true><<<dim3(n_mt, n_strips, ksplit), GT, G_SMEM, st>>>(bh_map, bl_map, ah_map, al_map, p);
@@ -425,11 +421,7 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
   p.C = C;
   p.ldc = ldc;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(gemm_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G_SMEM));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, (gemm_umma_kernel<false>), G_SMEM);
   {
     KpTimer timer(ctx, kp_ctx::T_CONV, st);
     gemm_umma_kernel<false><<<dim3(n_mt, n_strips, 1), GT, G_SMEM, st>>>(B.hi64, B.lo64, ah_map, al_map, p);

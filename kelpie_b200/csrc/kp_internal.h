@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <map>
 #include <string>
 #include <tuple>
@@ -120,6 +121,18 @@ struct kp_ctx {
     if (_e != cudaSuccess)                                                              \
       KP_FAIL(ctx, KP_ECUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), \
               __FILE__, __LINE__);                                                      \
+  } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per device and kernel; safe when several host threads (one per
+// context) reach the same launch site at once (the attribute call is idempotent, the flag is atomic)
+#define KP_SMEM_ONCE(ctx, func, bytes)                                                                          \
+  do {                                                                                                          \
+    static std::atomic<unsigned long long> _kp_done{0};                                                         \
+    const unsigned long long _kp_bit = 1ull << ((ctx)->device & 63);                                            \
+    if (!(_kp_done.load(std::memory_order_acquire) & _kp_bit)) {                                                \
+      KP_CUDA(ctx, cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)));      \
+      _kp_done.fetch_or(_kp_bit, std::memory_order_release);                                                    \
+    }                                                                                                           \
   } while (0)
 
 void kp_set_error(kp_ctx* ctx, const char* msg);

@@ -236,11 +236,7 @@ pass_kernel(const __grid_constant__ CUtensorMap emap, const __grid_constant__ CU
 
 template <int OP>
 int launch(kp_ctx* ctx, const CUtensorMap& qmap, const PassK& p, dim3 grid, cudaStream_t st) {
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(pass_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BYTES));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, (pass_kernel<OP>), SMEM_BYTES);
   KpTimer timer(ctx, kp_ctx::T_PASS, st);
   pass_kernel<OP><<<grid, N_THREADS, SMEM_BYTES, st>>>(ctx->ent_map, qmap, p);
   KP_LAUNCHED(ctx, 1);

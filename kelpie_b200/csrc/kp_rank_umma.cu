@@ -481,12 +481,8 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st) {
   p.target = a.target;
   p.best_act = best_act;
   p.act = act;
-  static bool configured_dev[64] = {}; bool& configured = configured_dev[ctx->device & 63];  /* the attribute is per device */
-  if (!configured) {
-    KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
-    KP_CUDA(ctx, cudaFuncSetAttribute(rank_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)R_SMEM));
-    configured = true;
-  }
+  KP_SMEM_ONCE(ctx, (rank_umma_kernel<false>), R_SMEM);
+  KP_SMEM_ONCE(ctx, (rank_umma_kernel<true>), R_SMEM);
   {
     KpTimer timer(ctx, kp_ctx::T_PASS, st);
     if (l2)
