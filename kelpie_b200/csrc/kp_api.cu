@@ -51,6 +51,11 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_x4 = value;
     return KP_OK;
   }
+  if (!strcmp(name, "umma_max_tps")) {
+    if (value < 0) KP_FAIL(ctx, KP_EINVAL, "umma_max_tps must be >= 0");
+    ctx->umma_max_tps = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "sv_dbg")) {
     ctx->sv_dbg = value;
     return KP_OK;

@@ -355,7 +355,11 @@ UPlan umma_plan(kp_ctx* ctx, int G) {
   // of the SMs the launch can occupy.  unit = CTAs that must be co-resident, units = clusters per strip.
   const int unit = u.quad ? 4 : (u.pair ? 2 : 1);
   const long long units = ((long long)u.n_qt * u.cc + unit - 1) / unit;
-  const int s = kp_plan_strips(units, sms / unit, u.n_tiles);
+  int s = kp_plan_strips(units, sms / unit, u.n_tiles);
+  if (ctx->umma_max_tps > 0) {  // bound the length of one fp32 accumulation chain in TMEM (kp_internal.h)
+    const int smin = (int)((u.n_tiles + ctx->umma_max_tps - 1) / ctx->umma_max_tps);
+    if (smin > s) s = smin;
+  }
   u.tps = (u.n_tiles + s - 1) / s;
   if (u.sv) u.tps = (u.tps + 1) & ~1;  // the S pair scores two entity tiles per MMA
   u.n_strips = (u.n_tiles + u.tps - 1) / u.tps;

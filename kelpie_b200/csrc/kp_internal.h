@@ -81,6 +81,11 @@ struct kp_ctx {
   int64_t umma_x4 = 2;   // rows wider than 256 floats: clusters of two pairs that compute S once; 2 = one pair scores, the other
                          // contracts (kp_flash_umma_sv.cu), 1 = both alternate (kp_flash_umma4.cu), 0 = independent pairs
   int64_t sv_dbg = 0;    // debug switches of kp_flash_umma_sv.cu
+  int64_t umma_max_tps = 256;  // entity tiles per strip of the tcgen05 fused pass at most (0 = no bound).  The tensor core's fp32
+                               // accumulation truncates: a running sum loses ~2^-24 of itself per accumulation, i.e. 1.9e-3 over
+                               // the 31 000 K-steps of a 500 000-entity strip -- enough, through Adagrad's scale-invariant update,
+                               // to move post-trained rows by 1e-3 (measured: the same candidate in batches of 2 / 64 / 300 / 1200).
+                               // 256 tiles = 2048 K-steps bound it at 1.2e-4 of O; the strips are merged in fp32 (round to nearest).
   int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
   int64_t umma_rotate = 1;  // rotating start of the entity walk (clusters share the table pass through L2)

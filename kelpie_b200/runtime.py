@@ -238,6 +238,49 @@ class Context:
             t = t.to(dtype)
         return t.pin_memory().to(self.device, non_blocking=True)
 
+    _NP = {torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64, torch.uint16: np.uint16}
+    PACK_LIMIT = 1 << 20  # small calls (explain-path batches) travel as ONE pinned block and ONE H2D copy
+
+    def dev_many(self, items):
+        """[(array | tensor | None, torch dtype)] -> device tensors.  Host arrays of a small call are packed into one
+        pinned staging block (two alternate, reused) and cross PCIe in a single copy instead of one pin + copy each;
+        large or already-pinned arrays and device tensors take the plain path."""
+        out, host, total = [None] * len(items), [], 0
+        for i, (a, dt) in enumerate(items):
+            if a is None:
+                continue
+            if isinstance(a, torch.Tensor):
+                out[i] = a.to(device=self.device, dtype=dt, non_blocking=True).contiguous()
+                continue
+            arr = np.ascontiguousarray(a, dtype=self._NP[dt])
+            host.append((i, arr, dt, total))
+            total += (arr.nbytes + 255) & ~255
+        if not host:
+            return out
+        if total > self.PACK_LIMIT:
+            for i, arr, dt, _ in host:
+                out[i] = self.dev(arr, dt)
+            return out
+        st = getattr(self, "_stage", None)
+        if st is None:
+            st = self._stage = {"buf": [None, None], "ev": [None, None], "n": 0}
+        k = st["n"] & 1
+        st["n"] += 1
+        if st["buf"][k] is None or st["buf"][k].numel() < total:
+            st["buf"][k] = torch.empty(max(total, 1 << 16), dtype=torch.uint8, pin_memory=True)
+            st["ev"][k] = torch.cuda.Event()
+        else:
+            st["ev"][k].synchronize()  # the copy that last read this block has finished (two calls ago)
+        hb = st["buf"][k].numpy()
+        for _, arr, _, off in host:
+            hb[off:off + arr.nbytes] = arr.reshape(-1).view(np.uint8)
+        blk = torch.empty(total, dtype=torch.uint8, device=self.device)
+        blk.copy_(st["buf"][k][:total], non_blocking=True)
+        st["ev"][k].record()
+        for i, arr, dt, off in host:
+            out[i] = blk[off:off + arr.nbytes].view(dt).view(arr.shape)
+        return out
+
     @property
     def launches(self):
         return int(self.lib.kp_launch_count(self.handle))
@@ -294,11 +337,10 @@ class Context:
 
     def filtered_rank(self, triples, mode, mimic_rows=None, flt_off=None, flt_ids=None, counters=False):
         """Returns (target_score[Q] f32, best_score[Q] f32, rank[Q] i64[, counters[Q,4] i32]) on device."""
-        t = self.dev(triples, torch.int32).view(-1, 3)
+        t, m, fo, fi = self.dev_many([(triples, torch.int32), (mimic_rows, torch.float32), (flt_off, torch.int64), (flt_ids, torch.int32)])
+        t = t.view(-1, 3)
         Q = t.shape[0]
-        m = None if mimic_rows is None else self.dev(mimic_rows, torch.float32).view(Q, self.D)
-        fo = None if flt_off is None else self.dev(flt_off, torch.int64)
-        fi = None if flt_ids is None else self.dev(flt_ids, torch.int32)
+        m = None if m is None else m.view(Q, self.D)
         if fo is not None and fi is None:
             fi = torch.zeros(1, dtype=torch.int32, device=self.device)
         ts = torch.empty(Q, dtype=torch.float32, device=self.device)
@@ -336,17 +378,14 @@ class Context:
                    fact_off=None, facts=None, pos_idx=None, neg_code=None):
         """Run one batch of C mimic post-trainings; returns the [C, D] post-trained rows (device).
         TransE: either pos / neg or the compact tables fact_off / facts / pos_idx (uint16) / neg_code (kelpie_b200.h)."""
-        init = self.dev(init_rows, torch.float32).view(-1, self.D)
+        staged = self.dev_many([(init_rows, torch.float32), (row_off, torch.int64), (rows_per_epoch, torch.int32),
+                                (pos, torch.int32), (neg, torch.int32), (pos_off, torch.int64), (pos_ids, torch.int32),
+                                (fact_off, torch.int64), (facts, torch.int32), (pos_idx, torch.uint16), (neg_code, torch.int32)])
+        init = staged[0].view(-1, self.D)
         C = init.shape[0]
         out = torch.empty_like(init)
-        keep = [init, out]
-
-        def d(a, dt):
-            if a is None:
-                return None
-            t = self.dev(a, dt)
-            keep.append(t)
-            return _ptr(t)
+        keep = [init, out] + staged
+        d = lambda i: None if staged[i] is None else _ptr(staged[i])
 
         if max_rows_per_epoch is None:  # host-known totals (pass them explicitly to avoid a device read)
             rpe = np.asarray(rows_per_epoch.cpu() if isinstance(rows_per_epoch, torch.Tensor) else rows_per_epoch)
@@ -355,10 +394,8 @@ class Context:
             ro = np.asarray(row_off.cpu() if isinstance(row_off, torch.Tensor) else row_off)
             total_rows = int(ro[-1])
         b = PTBatch(C, 1 if static_epochs else 0, int(max_rows_per_epoch), 0, int(total_rows),
-                    d(row_off, torch.int64), d(rows_per_epoch, torch.int32),
-                    d(pos, torch.int32), d(neg, torch.int32), d(pos_off, torch.int64), d(pos_ids, torch.int32),
-                    _ptr(init), _ptr(out), int(dropout_seed),
-                    d(fact_off, torch.int64), d(facts, torch.int32), d(pos_idx, torch.uint16), d(neg_code, torch.int32))
+                    d(1), d(2), d(3), d(4), d(5), d(6), _ptr(init), _ptr(out), int(dropout_seed),
+                    d(7), d(8), d(9), d(10))
         self._check(self.lib.kp_post_train_batch(self.handle, ctypes.byref(b), ctypes.byref(hp), self._stream()),
                     "kp_post_train_batch")
         self._keep = keep  # inputs must outlive the asynchronous kernels
