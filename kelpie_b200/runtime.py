@@ -239,7 +239,7 @@ class Context:
         return t.pin_memory().to(self.device, non_blocking=True)
 
     _NP = {torch.float32: np.float32, torch.int32: np.int32, torch.int64: np.int64, torch.uint16: np.uint16}
-    PACK_LIMIT = 1 << 20  # small calls (explain-path batches) travel as ONE pinned block and ONE H2D copy
+    PACK_LIMIT = int(os.environ.get("KP_PACK_LIMIT", 1 << 20))  # small calls (explain-path batches) travel as ONE pinned block and ONE H2D copy
 
     def dev_many(self, items):
         """[(array | tensor | None, torch dtype)] -> device tensors.  Host arrays of a small call are packed into one
