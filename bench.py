@@ -704,7 +704,10 @@ def collect_cpu_leg(leg, path, cfg, conv, ent_checksum, out, rows_p):
           "sample": f"the first {n} candidates of the same batch (post-training, all epochs, + filtered rank), {t_total:.1f} s of CPU time, "
                     f"run by a child process while the GPU warmed up" + (f"; one candidate = {conv} of them" if conv > 1 else "")}
     parity = None
-    if rows_p is not None and abs(r["ent_checksum"] - ent_checksum) <= 1e-9 * max(1.0, abs(ent_checksum)):
+    if any(float(x) != 0.0 for x in cfg.get("dropout", ())):
+        parity = {"skipped": "dropout > 0: the reference draws its masks from torch's generator, the device kernels from a counter-based "
+                             "one (DESIGN.md section 7) -- rows are comparable at rate 0 only (tests/test_gpu_parity.py, test_gpu_dbpedia50.py)"}
+    elif rows_p is not None and abs(r["ent_checksum"] - ent_checksum) <= 1e-9 * max(1.0, abs(ent_checksum)):
         jobs = r["jobs"]
         g_sc = np.array([float(out[j, 0]) for j in jobs], dtype=np.float64)
         g_rk = [int(out[j, 1]) for j in jobs]
