@@ -252,9 +252,8 @@ size_t kp_flash_part_rows(kp_ctx* ctx, int G) {
   const size_t few = (size_t)64 * G < (size_t)ctx->sm_count * 640 ? (size_t)64 * G : (size_t)ctx->sm_count * 640;
   if (few > rows) rows = few;
   if ((size_t)8 * G > rows) rows = (size_t)8 * G;
-  if (ctx->umma_max_tps > 0) {  // the bound on tiles per strip (kp_internal.h) sets a minimum number of strips
-    const size_t n_tiles = (size_t)((ctx->N + 127) / 128);
-    const size_t smin = (n_tiles + (size_t)ctx->umma_max_tps - 1) / (size_t)ctx->umma_max_tps + 1;  // + 1: even-tile rounding
+  {  // the bound on tiles per strip (kp_internal.h) sets a minimum number of strips (memory-capped: non-increasing in the rows)
+    const size_t smin = (size_t)kp_umma_min_strips(ctx, G) + 1;  // + 1: even-tile rounding
     if (smin * (size_t)G > rows) rows = smin * (size_t)G;
   }
   return rows + (size_t)G;  // slack for the CUDA-core plan's rounding (strips = ceil(2 SMs / query tiles))

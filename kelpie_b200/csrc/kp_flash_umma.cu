@@ -317,6 +317,27 @@ bool kp_flash_umma_usable(kp_ctx* ctx, int G) {
   return !ctx->force_simt && G >= ctx->umma_min_rows && ctx->D <= 512 && ctx->D % 4 == 0;
 }
 
+// Fewest strips the tcgen05 fused pass may cut the entity range into for g rows: ceil(tiles / umma_max_tps), relaxed so that the
+// strip partials (strips x g x D floats) stay within a quarter of the device memory (tables of many millions of entities).
+int kp_umma_min_strips(kp_ctx* ctx, long long g) {
+  if (ctx->umma_max_tps <= 0) return 1;
+  const long long n_tiles = (ctx->N + 127) / 128;
+  long long smin = (n_tiles + ctx->umma_max_tps - 1) / ctx->umma_max_tps;
+  if (ctx->total_mem == 0) {
+    size_t fr = 0, tot = 0;
+    if (cudaMemGetInfo(&fr, &tot) != cudaSuccess) {
+      cudaGetLastError();
+      tot = (size_t)64 << 30;
+    }
+    ctx->total_mem = (long long)tot;
+  }
+  const long long per_strip = (g > 0 ? g : 1) * (long long)ctx->D * 4;
+  long long by_mem = (ctx->total_mem / 4) / per_strip;
+  if (by_mem < 8) by_mem = 8;
+  if (smin > by_mem) smin = by_mem;
+  return (int)(smin < 1 ? 1 : smin);
+}
+
 namespace {
 struct UPlan {
   int KBs;     // 64-wide k-blocks of the S phase = ceil(D / 64)
@@ -356,10 +377,8 @@ UPlan umma_plan(kp_ctx* ctx, int G) {
   const int unit = u.quad ? 4 : (u.pair ? 2 : 1);
   const long long units = ((long long)u.n_qt * u.cc + unit - 1) / unit;
   int s = kp_plan_strips(units, sms / unit, u.n_tiles);
-  if (ctx->umma_max_tps > 0) {  // bound the length of one fp32 accumulation chain in TMEM (kp_internal.h)
-    const int smin = (int)((u.n_tiles + ctx->umma_max_tps - 1) / ctx->umma_max_tps);
-    if (smin > s) s = smin;
-  }
+  const int smin = kp_umma_min_strips(ctx, G);  // bound the length of one fp32 accumulation chain in TMEM (kp_internal.h)
+  if (smin > s) s = smin;
   u.tps = (u.n_tiles + s - 1) / s;
   if (u.sv) u.tps = (u.tps + 1) & ~1;  // the S pair scores two entity tiles per MMA
   u.n_strips = (u.n_tiles + u.tps - 1) / u.tps;

@@ -28,6 +28,8 @@ constexpr size_t G_SMEM = (size_t)NSLOT * SLOT + sizeof(GCtl) + 1024;
 
 struct GK_ {
   int M, N, KB, ksteps, n_tiles, tiles_per_strip, kb_per_split;  // kb_per_split > 0: split-K over blockIdx.z, C accumulated with reductions
+  int nt;  // columns of C per accumulator tile: 128, or up to 256 (a multiple of 16): A is then streamed once per 256 columns and an
+           // MMA reads 4 KB of A + nt / 64 KB of B per nt / 2 cycles -- 64 B/clk at nt = 256 instead of 96, under the shared-memory port
   float* C;
   long long ldc;
 };
@@ -79,8 +81,10 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
     }
     ptx::fence_barrier_init();
   }
+  const bool wide = p.nt > 128;
+  const uint32_t tm_stride = wide ? 256u : 128u, tm_cols = wide ? 512u : 256u;
   if (warp == 1) {
-    ptx::tmem_alloc2(&ctl->tmem_base, 256);
+    ptx::tmem_alloc2(&ctl->tmem_base, tm_cols);
     ptx::tmem_relinquish2();
   }
   ptx::tc_fence_before();
@@ -109,19 +113,32 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
       for (int i = 0; i < ntile; ++i)
         for (int kb = kb0; kb < kb1; ++kb) {
           load(&ah_map, &al_map, kb * (TF32 ? 32 : 64), mtile * 128, 16384, 2 * 32768);                          // my 128 rows of A
-          load(&bh64_map, &bl64_map, kb * (TF32 ? 32 : 64), (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the B tile
+          if (!wide) {
+            load(&bh64_map, &bl64_map, kb * (TF32 ? 32 : 64), (t0 + i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the B tile
+          } else {  // my nt / 2 <= 128 rows of the B tile as two 64-row boxes (rows past my half are loaded and not read)
+            const int s = use % NSLOT, col = kb * (TF32 ? 32 : 64), row = (t0 + i) * p.nt + (int)crank * (p.nt / 2);
+            ptx::mbar_wait(&ctl->empty[s], ((use / NSLOT) & 1) ^ 1);
+            if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], 2 * 32768);
+            const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&ctl->full[s]), 0);
+            uint8_t* dst = ring + (size_t)s * SLOT;
+            ptx::tma_load_2d_pair(dst, &bh64_map, bar, col, row);
+            ptx::tma_load_2d_pair(dst + 8192, &bh64_map, bar, col, row + 64);
+            ptx::tma_load_2d_pair(dst + 16384, &bl64_map, bar, col, row);
+            ptx::tma_load_2d_pair(dst + 24576, &bl64_map, bar, col, row + 64);
+            ++use;
+          }
         }
     }
   } else if (warp == 1) {
     if (lane == 0 && leader) {
       const uint32_t fmt = TF32 ? 2u : 1u;  // cute::UMMA::F16F32Format: BF16 = 1, TF32 = 2
-      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((128u >> 3) << 17) | ((256u >> 4) << 24);
+      const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | (((uint32_t)p.nt >> 3) << 17) | ((256u >> 4) << 24);
       const uint32_t ring_a = ptx::smem_u32(ring);
       const uint64_t DK = udesc(0, 16, 1024);
       uint32_t use = 0;
       for (int i = 0; i < ntile; ++i) {
         const int sb = i & 1;
-        const uint32_t d_s = tm + sb * 128;
+        const uint32_t d_s = tm + sb * tm_stride;
         if (i >= 2) {
           ptx::mbar_wait_cluster(&ctl->s_free[sb], ((i >> 1) - 1) & 1);
           ptx::tc_fence_after();
@@ -131,7 +148,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
           ptx::mbar_wait(&ctl->full[(use + 1) % NSLOT], ((use + 1) / NSLOT) & 1);
           ptx::tc_fence_after();
           const uint32_t a_hi = ring_a + (use % NSLOT) * SLOT, a_lo = a_hi + 16384;
-          const uint32_t b_hi = ring_a + ((use + 1) % NSLOT) * SLOT, b_lo = b_hi + 8192;
+          const uint32_t b_hi = ring_a + ((use + 1) % NSLOT) * SLOT, b_lo = b_hi + (wide ? 16384 : 8192);
           const uint64_t ah = DK + (a_hi >> 4), al = DK + (a_lo >> 4), bh = DK + (b_hi >> 4), bl = DK + (b_lo >> 4);
 #pragma unroll
           for (int kk = 0; kk < 4; ++kk) {
@@ -161,12 +178,12 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
     const uint32_t s_free_leader0 = ptx::mapa_u32(ptx::smem_u32(&ctl->s_free[0]), 0);
     for (int i = 0; i < ntile; ++i) {
       const int sb = i & 1;
-      const int n0 = (t0 + i) * 128;
+      const int n0 = (t0 + i) * p.nt;
       ptx::mbar_wait(&ctl->s_full[sb], (i >> 1) & 1);
       ptx::tc_fence_after();
-      const uint32_t s_addr = tm + sb * 128 + lane_off;
+      const uint32_t s_addr = tm + sb * tm_stride + lane_off;
 #pragma unroll 1
-      for (int c0 = 0; c0 < 128; c0 += 32) {
+      for (int c0 = 0; c0 < p.nt; c0 += 32) {
         uint32_t r[32];
         ptx::tmem_ld_32x32(s_addr + c0, r);
         ptx::tmem_ld_wait();
@@ -192,7 +209,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
   ptx::tc_fence_before();
   __syncthreads();
   ptx::cluster_sync_all();
-  if (warp == 1) ptx::tmem_dealloc2(tm, 256);
+  if (warp == 1) ptx::tmem_dealloc2(tm, tm_cols);
 }
 
 // fp32 [rows, cols] (ld) -> bf16 hi / lo [rows_pad, cols_pad] (zero padded)
@@ -331,6 +348,7 @@ int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, in
   p.N = Nc;
   p.KB = Kpad / epb;
   p.ksteps = (K + epb / 4 - 1) / (epb / 4);  // one MMA covers a quarter of a k-block (32 bytes): 16 bf16 or 8 tf32
+  p.nt = 128;
   p.n_tiles = (N + 127) / 128;
   const int s = kp_plan_strips(n_mt / 2, ctx->sm_count / 2, p.n_tiles);
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;
@@ -415,7 +433,10 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   p.KB = B.Kpad / 64;
   p.ksteps = (B.K + 15) / 16;
   p.kb_per_split = 0;
-  p.n_tiles = (B.N + 127) / 128;
+  // wide accumulator tiles (option gemm_wide): one tile of N rounded up to 16 when N <= 256 (the forward Linear layer: N = 200 ->
+  // 208 columns instead of two tiles of 128), 256 columns otherwise (the backward one: N = 9728)
+  p.nt = (ctx->gemm_wide && B.N > 128) ? (B.N <= 256 ? ((B.N + 15) / 16) * 16 : 256) : 128;
+  p.n_tiles = (B.N + p.nt - 1) / p.nt;
   const int s = kp_plan_strips(n_mt / 2, ctx->sm_count / 2, p.n_tiles);
   p.tiles_per_strip = (p.n_tiles + s - 1) / s;
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;

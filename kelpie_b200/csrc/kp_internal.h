@@ -27,6 +27,7 @@ struct kp_ctx {
   int D = 0;       // floats per embedding row
   int norm = 2;
   int sm_count = 148;
+  long long total_mem = 0;  // device memory in bytes (queried on first use)
   const float* ent = nullptr;  // [N, D]
   const float* rel = nullptr;  // [R2, D]
   bool own_ent = false, own_rel = false;
@@ -86,6 +87,7 @@ struct kp_ctx {
                                // the 31 000 K-steps of a 500 000-entity strip -- enough, through Adagrad's scale-invariant update,
                                // to move post-trained rows by 1e-3 (measured: the same candidate in batches of 2 / 64 / 300 / 1200).
                                // 256 tiles = 2048 K-steps bound it at 1.2e-4 of O; the strips are merged in fp32 (round to nearest).
+  int64_t gemm_wide = 1;  // ConvE Linear layer GEMMs with accumulator tiles of up to 256 columns (kp_gemm_umma.cu)
   int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
   int64_t umma_rotate = 1;  // rotating start of the entity walk (clusters share the table pass through L2)
@@ -246,6 +248,7 @@ int kp_flash_umma_sv_sms(kp_ctx* ctx);
 int kp_flash_umma_sv_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensorMap& ql_map, int G, int KBs, int ngroup,
                             int n_qt, int n_strips, int tps, int mode, float* part_m, float* part_l, float* part_O,
                             cudaStream_t st);
+int kp_umma_min_strips(kp_ctx* ctx, long long g);
 int kp_umma_tables(kp_ctx* ctx, cudaStream_t st);
 int kp_umma_split_rows(kp_ctx* ctx, const float* mat, int G, long long Gpad, CUtensorMap* hi_map, CUtensorMap* lo_map,
                        cudaStream_t st);
