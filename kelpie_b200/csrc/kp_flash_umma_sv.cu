@@ -47,9 +47,7 @@ struct SVCtl {
   uint64_t full[NSLOT_S], empty[NSLOT_S];
   uint64_t s_full[2], s_free[2], pin_empty[2];
   uint64_t pin_full[2], p_ready[2], pv_done[2];
-  uint64_t pin_all[2];  // V leader: all 256 rows of a P tile delivered (both S SMs arrive here directly)
   uint64_t o_done;
-  uint32_t need[2];     // V leader: some row of the tile in buffer b carries a rescale factor != 1 (set by the S SM's thread)
   uint32_t tmem_base;
   int start, start_local;
 };
@@ -186,8 +184,6 @@ flash_umma_sv_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_co
       ptx::mbar_init(&ctl->pin_full[b], 128);
       ptx::mbar_init(&ctl->p_ready[b], 256);
       ptx::mbar_init(&ctl->pv_done[b], 1);
-      ptx::mbar_init(&ctl->pin_all[b], 256);
-      ctl->need[b] = 0;
     }
     ptx::mbar_init(&ctl->o_done, 1);
     // rotating start (see kp_flash_umma4.cu): clusters that begin mid-wave join the others where they are
@@ -324,17 +320,10 @@ flash_umma_sv_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_co
         for (int t = 0; t < 2 * npair; ++t) {
           const int b = t & 1;
           {
-            // the tile is contracted as soon as its 256 rows have landed: the S SMs' threads arrive here directly; the V SMs'
-            // row threads (p_ready) are waited for only when some row asked for a rescale of O (rare: lazy reference max)
             const long long a = clock64();
-            ptx::mbar_wait_cluster(&ctl->pin_all[b], (t >> 1) & 1);
-            if (*(volatile uint32_t*)&ctl->need[b]) {
-              ptx::mbar_wait_cluster(&ctl->p_ready[b], (t >> 1) & 1);
-              *(volatile uint32_t*)&ctl->need[b] = 0;
-            }
+            ptx::mbar_wait_cluster(&ctl->p_ready[b], (t >> 1) & 1);
             w_dep += clock64() - a;
           }
-          ptx::fence_proxy_async();  // P was written through the generic proxy (remote stores), the MMA reads it through the async one
           ptx::tc_fence_after();
           for (int g = 0; g < ngroup; ++g)
             for (int eh = 0; eh < 2; ++eh) {
@@ -378,8 +367,6 @@ flash_umma_sv_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_co
       const uint32_t pdst0 = ptx::mapa_u32(ptx::smem_u32(pbuf) + (uint32_t)row * 16u, peer);
       const uint32_t hdr0 = ptx::mapa_u32(ptx::smem_u32(phdr) + (uint32_t)row * 4u, peer);
       const uint32_t pin_full_peer = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_full[0]), peer);
-      const uint32_t pin_all_vlead = ptx::mapa_u32(ptx::smem_u32(&ctl->pin_all[0]), 2);
-      const uint32_t need_vlead = ptx::mapa_u32(ptx::smem_u32(&ctl->need[0]), 2);
       float m_ref = -INFINITY, l_run = 0.f;
       for (int k = 0; k < npair; ++k) {
         const int j = k & 1;
@@ -410,10 +397,8 @@ flash_umma_sv_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_co
           else
             p_tile_ship<false>(r, m_ref, l_run, factor, pdst, &ctl->pin_empty[u], k > 0, (k - 1) & 1, !(p.dbg & 64));
           st_cluster_f32(hdr0 + (uint32_t)u * PHDR, factor);
-          if (factor != 1.f) asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(need_vlead + (uint32_t)u * 4u), "r"(1u) : "memory");
           fence_proxy_async_all();                                     // my stores precede the V SM's tcgen05.mma reads
-          ptx::mbar_arrive_cluster(pin_full_peer + (uint32_t)u * 8u);  // release: my row of tile 2k+u is delivered (row threads)
-          ptx::mbar_arrive_cluster(pin_all_vlead + (uint32_t)u * 8u);  // ... and counted for the MMA issuer
+          ptx::mbar_arrive_cluster(pin_full_peer + (uint32_t)u * 8u);  // release: my row of tile 2k+u is delivered
         }
       }
       if (g < p.G) {
