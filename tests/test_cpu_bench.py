@@ -55,12 +55,17 @@ def test_reference_arm_prints_the_contract_line(port):
     env = dict(os.environ, KP_REFERENCE_BUDGET_S="120")
     if port:
         env["KP_REFERENCE_PORT"] = "1"
-    p = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "synthetic_complex_small",
-                        "--steps", "3", "--warmup", "1"], capture_output=True, text=True, timeout=600, env=env)
+    # run bench.py as __main__ inside a wrapper that afterwards reports what the process imported / mapped
+    wrapper = ("import sys, runpy; sys.argv = ['bench.py', '--impl', 'reference', '--workload', 'synthetic_complex_small', '--steps', '3', "
+               "'--warmup', '1']; runpy.run_path(%r, run_name='__main__'); "
+               "print('PRODUCT_IMPORTED', any(m.startswith('kelpie_b200') for m in sys.modules), "
+               "'libkelpie_b200' in open('/proc/self/maps').read())" % os.path.join(ROOT, "bench.py"))
+    p = subprocess.run([sys.executable, "-c", wrapper], capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
     assert p.returncode == 0, p.stderr[-2000:]
-    line = json.loads(p.stdout.strip().splitlines()[-1])
+    lines = p.stdout.strip().splitlines()
+    assert lines[-1] == "PRODUCT_IMPORTED False False"  # no module of kelpie_b200 imported, its .so not mapped
+    line = json.loads(lines[-2])
     assert line["impl"] == "reference" and line["steps"] == 3 and line["unit"] == "candidates/s" and line["higher_is_better"]
     assert line["cpu_baseline"]["kind"] == ("port" if port else "reference") and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert line["value"] > 0 and abs(line["ms_per_step"] * line["value"] - 1000.0) < 1e-6
-    assert "kelpie_b200" not in p.stderr  # the arm imports nothing of the product
