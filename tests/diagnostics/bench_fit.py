@@ -2,7 +2,7 @@
 device time per epoch and per step, algorithmic HBM bytes of the dense Adam update, next to the oracle
 restatement (= the reference's torch loop) on the host cores for a bounded sample of steps."""
 import sys, os, json, time, argparse
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from kelpie_b200 import plans, runtime
 from kelpie_b200.data import Dataset

@@ -1,7 +1,7 @@
 """Step-level comparison of the device ConvE trainer (kp_conve_fit_*) with the oracle restatement on the golden KG:
 per-tensor max error relative to the tensor's max |.| after 1, 2, 5, 24 steps."""
 import sys, os
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from tests.golden_util import GOLDEN, seed_all
 from oracle import kelpie_oracle as ko

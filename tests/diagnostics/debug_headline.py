@@ -1,7 +1,7 @@
 """Where does the 1M x 512 post-training deviate from the oracle?  Rows after 1 / 2 / 3 epochs: tcgen05 S/V kernel,
 round-1 cluster kernel, CUDA-core pass, oracle (fp32 CPU) and an fp64 restatement of the oracle."""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 from oracle import kelpie_oracle as ko
 from kelpie_b200 import plans, runtime

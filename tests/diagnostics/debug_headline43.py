@@ -1,6 +1,6 @@
 """43 epochs at 1M x 512 on the first candidates of the bench batch: which paths drift from the fp64 oracle, and when?"""
 import os, sys
-sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 import numpy as np, torch
 import bench
 from oracle import kelpie_oracle as ko
