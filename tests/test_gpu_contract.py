@@ -94,3 +94,18 @@ def test_quad_matches_pair_kernel(quad):
     assert np.abs(out[quad][1] * s - out[0][1]).max() <= 1e-5 * np.abs(out[0][1]).max()
     assert np.abs(out[quad][2] * s[:, None] - out[0][2]).max() <= 1e-5 * np.abs(out[0][2]).max()
     ctx.close()
+
+
+@pytest.mark.parametrize("N,G", [(100, 300), (130, 257), (255, 512), (257, 300), (1000, 1), (77, 130)])
+def test_contract_tiny_tables_and_ragged_rows(N, G):
+    """S/V kernel edge cases: fewer entities than one tile pair (the second tile of the pair is all padding), a table that
+    ends just past a tile boundary, row counts that are not a multiple of the 256-row cluster tile, a single row."""
+    from kelpie_b200 import runtime
+    rng = np.random.default_rng(N * 1000 + G)
+    D = 512
+    ent = (rng.standard_normal((N, D)) * 0.3).astype(np.float32)
+    q = (rng.standard_normal((G, D)) * 0.25).astype(np.float32)
+    ctx = runtime.Context("ComplEx", ent, np.zeros((2, D), np.float32))
+    for mode in (0, 1):
+        _check(ctx, q if mode == 0 else q * 0.2, ent, mode)
+    ctx.close()
