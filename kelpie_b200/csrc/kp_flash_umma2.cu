@@ -22,20 +22,25 @@ namespace {
 
 constexpr int UT = 192;
 constexpr int SLOT = 32768;
-constexpr int NSLOT = 6;
+constexpr int NSLOT = 6;   // ring slots when the query k-blocks are streamed with every entity tile
+constexpr int NBUF = 7;    // 32 KB blocks of shared memory in all: resident query k-blocks (<= 4) + ring when they are kept
 constexpr float RESCALE_TAU = 8.0f;
 
 struct UCtl2 {
-  uint64_t full[NSLOT], empty[NSLOT];
+  uint64_t full[NBUF], empty[NBUF];
   uint64_t s_full[2];
   uint64_t p_full, pv_done, o_done;
+  uint64_t q_full;  // resident-query mode: my query tile (all k-blocks, hi / lo) has landed
   uint32_t tmem_base;
   int start, start_local;
 };
-constexpr size_t U2_SMEM = (size_t)NSLOT * SLOT + sizeof(UCtl2) + 1024;
+constexpr size_t U2_SMEM = (size_t)NBUF * SLOT + sizeof(UCtl2) + 1024;
+static_assert(U2_SMEM <= 232448, "shared memory budget of one CTA");
 
 struct UK2 {
   int G, N, D, KB, n_tiles, tiles_per_strip, groups_per_chunk, mode;
+  int qres;  // keep the query tile (KB <= 4 k-blocks of 32 KB) resident instead of re-streaming it with every entity tile: with a
+             // short K the S phase otherwise fills shared memory at 77 B/clk next to 96 B/clk of operand reads (port: 128 B/clk)
   float* part_m;
   float* part_l;
   float* part_O;
@@ -58,8 +63,7 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
                    const __grid_constant__ CUtensorMap qh_map, const __grid_constant__ CUtensorMap ql_map, const UK2 p) {
   extern __shared__ uint8_t uraw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(uraw) + 1023) & ~uintptr_t(1023));
-  uint8_t* ring = sm;
-  UCtl2* ctl = reinterpret_cast<UCtl2*>(sm + (size_t)NSLOT * SLOT);
+  UCtl2* ctl = reinterpret_cast<UCtl2*>(sm + (size_t)NBUF * SLOT);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int strip = blockIdx.y, qtile = blockIdx.x, chunk = blockIdx.z;  // the SM pair spans x
@@ -75,13 +79,19 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
   // chunk its last dim group is contracted with N = the dims that are left, rounded up to 32 (each SM then
   // stages n_last / 2 dims, starting at the group's base + rank * n_last / 2).
   const int ksteps = (p.D + 15) / 16;
+  const bool qres = p.qres != 0;
+  uint8_t* qbuf = sm;                                           // resident mode: k-block kb of my query tile at kb * SLOT (hi | lo)
+  uint8_t* ring = qres ? sm + (size_t)p.KB * SLOT : sm;
+  const int nring = qres ? NBUF - p.KB : NSLOT;
+  const int kb2n = (p.KB + 1) >> 1;                             // resident mode: entity k-blocks travel two per ring slot
   const int n_last = (gridDim.z == 1) ? min(128, ((p.D - 128 * (ngroup - 1) + 31) / 32) * 32) : 128;
 
   if (tid == 0) {
-    for (int s = 0; s < NSLOT; ++s) {
+    for (int s = 0; s < NBUF; ++s) {
       ptx::mbar_init(&ctl->full[s], 1);
       ptx::mbar_init(&ctl->empty[s], 1);
     }
+    ptx::mbar_init(&ctl->q_full, 1);
     for (int b = 0; b < 2; ++b) ptx::mbar_init(&ctl->s_full[b], 1);
     ptx::mbar_init(&ctl->p_full, 256);  // 128 softmax threads of each CTA (used in the leader only)
     ptx::mbar_init(&ctl->pv_done, 1);
@@ -119,8 +129,8 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       uint32_t use = 0;
       // bytes_pair = bytes the two CTAs together deliver for this slot use (armed on the leader's barrier)
       auto load = [&](const CUtensorMap* hi, const CUtensorMap* lo, int col, int row, uint32_t lo_off, uint32_t bytes_pair) {
-        const int s = use % NSLOT;
-        ptx::mbar_wait(&ctl->empty[s], ((use / NSLOT) & 1) ^ 1);
+        const int s = use % nring;
+        ptx::mbar_wait(&ctl->empty[s], ((use / nring) & 1) ^ 1);
         if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], bytes_pair);
         const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&ctl->full[s]), 0);
         uint8_t* dst = ring + (size_t)s * SLOT;
@@ -128,12 +138,37 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
         ptx::tma_load_2d_pair(dst + lo_off, lo, bar, col, row);
         ++use;
       };
+      if (qres) {  // my query tile, once
+        if (leader) ptx::mbar_arrive_expect_tx(&ctl->q_full, (uint32_t)(2 * p.KB) * SLOT);
+        const uint32_t qbar = ptx::mapa_u32(ptx::smem_u32(&ctl->q_full), 0);
+        for (int kb = 0; kb < p.KB; ++kb) {
+          ptx::tma_load_2d_pair(qbuf + (size_t)kb * SLOT, &qh_map, qbar, kb * 64, qtile * 128);
+          ptx::tma_load_2d_pair(qbuf + (size_t)kb * SLOT + 16384, &ql_map, qbar, kb * 64, qtile * 128);
+        }
+      }
       for (int i = 0; i <= ntile; ++i) {
-        if (i < ntile)
-          for (int kb = 0; kb < p.KB; ++kb) {
-            load(&qh_map, &ql_map, kb * 64, qtile * 128, 16384, 2 * 32768);                         // my query tile
-            load(&eh64_map, &el64_map, kb * 64, tile_of(i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the entities
+        if (i < ntile) {
+          if (!qres) {
+            for (int kb = 0; kb < p.KB; ++kb) {
+              load(&qh_map, &ql_map, kb * 64, qtile * 128, 16384, 2 * 32768);                         // my query tile
+              load(&eh64_map, &el64_map, kb * 64, tile_of(i) * 128 + (int)crank * 64, 8192, 2 * 16384);  // my half of the entities
+            }
+          } else {
+            for (int k2 = 0; k2 < kb2n; ++k2) {  // my half of the entities, two k-blocks per slot: [hi | lo | hi | lo] x 8 KB
+              const int nk = min(2, p.KB - 2 * k2);
+              const int s = use % nring;
+              ptx::mbar_wait(&ctl->empty[s], ((use / nring) & 1) ^ 1);
+              if (leader) ptx::mbar_arrive_expect_tx(&ctl->full[s], (uint32_t)(2 * nk) * 16384);
+              const uint32_t bar = ptx::mapa_u32(ptx::smem_u32(&ctl->full[s]), 0);
+              uint8_t* dst = ring + (size_t)s * SLOT;
+              for (int h = 0; h < nk; ++h) {
+                ptx::tma_load_2d_pair(dst + h * 16384, &eh64_map, bar, (2 * k2 + h) * 64, tile_of(i) * 128 + (int)crank * 64);
+                ptx::tma_load_2d_pair(dst + h * 16384 + 8192, &el64_map, bar, (2 * k2 + h) * 64, tile_of(i) * 128 + (int)crank * 64);
+              }
+              ++use;
+            }
           }
+        }
         if (i > 0)
           for (int g = 0; g < ngroup; ++g)  // my half of the group's dims (64, or n_last / 2 of a trimmed last group)
             load(&eh_map, &el_map, (box0 + 2 * g) * 64 + (int)crank * (g == ngroup - 1 ? n_last / 2 : 64), tile_of(i - 1) * 128, 16384,
@@ -150,15 +185,20 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
       // descriptor templates: only the 14-bit start-address field changes between MMAs
       const uint64_t DK = udesc(0, 16, 1024), DMN = udesc(0, 16384, 1024);
       uint32_t use = 0;
-      auto wait_slot = [&](uint32_t u) { ptx::mbar_wait(&ctl->full[u % NSLOT], (u / NSLOT) & 1); };
-      auto release = [&](uint32_t u) { ptx::umma2_commit_mc(&ctl->empty[u % NSLOT], 3); };
+      auto wait_slot = [&](uint32_t u) { ptx::mbar_wait(&ctl->full[u % nring], (u / nring) & 1); };
+      auto release = [&](uint32_t u) { ptx::umma2_commit_mc(&ctl->empty[u % nring], 3); };
+      const uint32_t q_a = ptx::smem_u32(qbuf);
+      if (qres) {
+        ptx::mbar_wait(&ctl->q_full, 0);
+        ptx::tc_fence_after();
+      }
       auto pv = [&](int t) {
         ptx::mbar_wait_cluster(&ctl->p_full, t & 1);
         ptx::tc_fence_after();
         for (int g = 0; g < ngroup; ++g) {
           wait_slot(use);
           ptx::tc_fence_after();
-          const uint32_t e_hi = ring_a + (use % NSLOT) * SLOT, e_lo = e_hi + 16384;
+          const uint32_t e_hi = ring_a + (use % nring) * SLOT, e_lo = e_hi + 16384;
           const uint32_t d_o = TM_O + g * 128;
           const uint32_t p_t = TM_S + (t & 1) * 128;
           const uint32_t idesc_g = (g == ngroup - 1) ? idesc_pv_last : idesc_pv;
@@ -180,23 +220,46 @@ flash_umma2_kernel(const __grid_constant__ CUtensorMap eh_map, const __grid_cons
         const int sb = i & 1;
         const uint32_t d_s = TM_S + sb * 128;
         if (p.cursor && chunk == 0) *(volatile int*)&p.cursor[blockIdx.y] = tile_of(i) - t0;
-        for (int kb = 0; kb < p.KB; ++kb) {
-          wait_slot(use);
-          wait_slot(use + 1);
-          ptx::tc_fence_after();
-          const uint32_t q_hi = ring_a + (use % NSLOT) * SLOT, q_lo = q_hi + 16384;
-          const uint32_t e_hi = ring_a + ((use + 1) % NSLOT) * SLOT, e_lo = e_hi + 8192;
-          const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
+        if (!qres) {
+          for (int kb = 0; kb < p.KB; ++kb) {
+            wait_slot(use);
+            wait_slot(use + 1);
+            ptx::tc_fence_after();
+            const uint32_t q_hi = ring_a + (use % nring) * SLOT, q_lo = q_hi + 16384;
+            const uint32_t e_hi = ring_a + ((use + 1) % nring) * SLOT, e_lo = e_hi + 8192;
+            const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            if (kb * 4 + kk >= ksteps) break;  // only zero padding beyond D
-            ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
-            ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
-            ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc_s, 1u);
+            for (int kk = 0; kk < 4; ++kk) {
+              if (kb * 4 + kk >= ksteps) break;  // only zero padding beyond D
+              ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
+              ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
+              ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc_s, 1u);
+            }
+            release(use);
+            release(use + 1);
+            use += 2;
           }
-          release(use);
-          release(use + 1);
-          use += 2;
+        } else {
+          for (int k2 = 0; k2 < kb2n; ++k2) {
+            wait_slot(use);
+            ptx::tc_fence_after();
+            const int nk = min(2, p.KB - 2 * k2);
+            for (int h = 0; h < nk; ++h) {
+              const int kb = 2 * k2 + h;
+              const uint32_t q_hi = q_a + (uint32_t)kb * SLOT, q_lo = q_hi + 16384;
+              const uint32_t e_hi = ring_a + (use % nring) * SLOT + (uint32_t)h * 16384u, e_lo = e_hi + 8192;
+              const uint64_t ah = DK + (q_hi >> 4), al = DK + (q_lo >> 4), bh = DK + (e_hi >> 4), bl = DK + (e_lo >> 4);
+#pragma unroll
+              for (int kk = 0; kk < 4; ++kk) {
+                if (kb * 4 + kk >= ksteps) break;  // only zero padding beyond D
+                ptx::umma2_bf16(d_s, ah + kk * 2, bh + kk * 2, idesc_s, (kb > 0 || kk > 0) ? 1u : 0u);
+                ptx::umma2_bf16(d_s, ah + kk * 2, bl + kk * 2, idesc_s, 1u);
+                ptx::umma2_bf16(d_s, al + kk * 2, bh + kk * 2, idesc_s, 1u);
+              }
+            }
+            release(use);
+            ++use;
+          }
         }
         ptx::umma2_commit_mc(&ctl->s_full[sb], 3);
         if (i > 0) pv(i - 1);
@@ -284,6 +347,7 @@ int kp_flash_umma2_launch(kp_ctx* ctx, const CUtensorMap& qh_map, const CUtensor
   p.tiles_per_strip = tps;
   p.groups_per_chunk = groups_per_chunk;
   p.mode = mode;
+  p.qres = (ctx->umma_qres != 0 && KBs <= 4) ? 1 : 0;
   p.part_m = part_m;
   p.part_l = part_l;
   p.part_O = part_O;

@@ -87,6 +87,7 @@ struct kp_ctx {
                                // the 31 000 K-steps of a 500 000-entity strip -- enough, through Adagrad's scale-invariant update,
                                // to move post-trained rows by 1e-3 (measured: the same candidate in batches of 2 / 64 / 300 / 1200).
                                // 256 tiles = 2048 K-steps bound it at 1.2e-4 of O; the strips are merged in fp32 (round to nearest).
+  int64_t umma_qres = 1;  // pair kernel (rows of <= 256 floats): query tile resident in shared memory (kp_flash_umma2.cu)
   int64_t gemm_wide = 1;  // ConvE Linear layer GEMMs with accumulator tiles of up to 256 columns (kp_gemm_umma.cu)
   int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
