@@ -56,6 +56,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_max_tps = value;
     return KP_OK;
   }
+  if (!strcmp(name, "conv_split")) {
+    ctx->conv_split = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "umma_qres")) {
     ctx->umma_qres = value;
     return KP_OK;

@@ -6,7 +6,13 @@
 #include "kp_ptx.cuh"
 #include "kp_dropout.cuh"
 
+#include <cuda_bf16.h>
+
 namespace {
+
+__device__ __forceinline__ uint32_t pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
 
 
 struct ConvK {
@@ -19,7 +25,9 @@ struct ConvK {
   const int32_t* mimic_index;  // row of `mimic` used by query q (NULL: row q)
   const float *conv_w, *conv_b, *fc_w, *fc_b, *bn1, *bn2, *bn3;
   float* x_out;      // [Q, D]
-  float* feat_out;   // nullable [Q, hidden]: post-ReLU feature maps (kept for the backward pass)
+  float* feat_out;   // [Q, hidden]: post-ReLU feature maps (kept for the backward pass), unless hi_out is set:
+  __nv_bfloat16 *hi_out, *lo_out;  // the same as the Linear GEMM's split operand, bf16 [.., kpad] each (x = hi + lo + O(2^-16 x))
+  int kpad;
   // training-mode dropout (conve.py:34-36,140-152; active during post-training, model.py:114-125)
   const int32_t* drop_ids;  // NULL = eval mode; else the pair id keying the masks of query q
   unsigned long long seed;
@@ -87,6 +95,36 @@ __global__ void __launch_bounds__(CV_CONV_THREADS) conve_conv_kernel(const ConvK
       a2[f] = a2s[c0 + f];
       b2[f] = b2s[c0 + f];
     }
+    if (p.hi_out) {  // a lane owns two neighbouring positions: one 4-byte store per filter and half (hi = bf16(x), lo = bf16(x - hi))
+      uint32_t* hi = reinterpret_cast<uint32_t*>(p.hi_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
+      uint32_t* lo = reinterpret_cast<uint32_t*>(p.lo_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
+      for (int pp = lane; pp < per_f / 2; pp += 32) {  // per_f = 38 * W2 is even
+        const int pos = 2 * pp, y0 = pos / W2, y1 = (pos + 1) / W2;
+        const float* tap0 = img + pos + 2 * y0;
+        const float* tap1 = img + pos + 1 + 2 * y1;
+        float acc0[4] = {bias[0], bias[1], bias[2], bias[3]}, acc1[4] = {bias[0], bias[1], bias[2], bias[3]};
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float v0 = tap0[dy * H + dx], v1 = tap1[dy * H + dx];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) {
+              acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v0, acc0[f]);
+              acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v1, acc1[f]);
+            }
+          }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) {
+          const float x0 = fmaxf(__fmaf_rn(acc0[f], a2[f], b2[f]), 0.f), x1 = fmaxf(__fmaf_rn(acc1[f], a2[f], b2[f]), 0.f);
+          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+          hi[(size_t)f * (per_f / 2) + pp] = pack_bf16x2(h0, h1);
+          lo[(size_t)f * (per_f / 2) + pp] =
+              pack_bf16x2(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+        }
+      }
+      continue;
+    }
     float* out = p.feat_out + (size_t)q * p.hidden + (size_t)c0 * per_f;
     for (int pos = lane; pos < per_f; pos += 32) {
       const int y = pos / W2;
@@ -104,6 +142,11 @@ __global__ void __launch_bounds__(CV_CONV_THREADS) conve_conv_kernel(const ConvK
       for (int f = 0; f < 4; ++f) out[(size_t)f * per_f + pos] = fmaxf(__fmaf_rn(acc[f], a2[f], b2[f]), 0.f);
     }
   }
+  if (p.hi_out)  // zero columns up to the GEMM's k-block boundary
+    for (int k = p.hidden + tid; k < p.kpad; k += CV_CONV_THREADS) {
+      p.hi_out[(size_t)q * p.kpad + k] = __float2bfloat16_rn(0.f);
+      p.lo_out[(size_t)q * p.kpad + k] = __float2bfloat16_rn(0.f);
+    }
 }
 
 // Stage 3: x = ReLU(BN3(dropout(raw + fc_b)))   (stage 2 is the Linear GEMM, kp_gemm.cu)
@@ -183,6 +226,12 @@ int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
   return KP_OK;
 }
 
+bool kp_conve_fc_umma(const kp_ctx* ctx, int M) {
+  return ctx->conv_split && ctx->umma_fc && !ctx->force_simt && ctx->cv.fc_fwd.ready && M >= 128;
+}
+size_t kp_conve_feat_half_bytes(const kp_ctx* ctx, int M) { return kp_gemm_umma_a_bytes(M, ctx->cv.fc_fwd); }
+int kp_conve_feat_kpad(const kp_ctx* ctx) { return ctx->cv.fc_fwd.Kpad; }
+
 int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st) {
   const int D = ctx->D, hidden = ctx->cv.hidden;
   const kp_umma_b& B = forward ? ctx->cv.fc_fwd : ctx->cv.fc_bwd;
@@ -227,15 +276,19 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
   p.x_out = x_out;
   p.feat_out = feat_out;
   // feature maps go to the caller's buffer (kept for the backward pass) or to scratch, in chunks
-  const int chunk = feat_out ? Q : (Q < 4096 ? Q : 4096);
-  float* scratch = feat_out;
+  const int chunk = feat_out ? Q : (Q < 16384 ? Q : 16384);
+  const bool split_first = kp_conve_fc_umma(ctx, chunk);
+  const size_t fp32_bytes = (size_t)chunk * p.hidden * sizeof(float) + 1024;
+  const size_t half = split_first ? kp_conve_feat_half_bytes(ctx, chunk) : 0;
+  char* scratch = reinterpret_cast<char*>(feat_out);
   if (!feat_out) {
-    int rc = kp_ws_reserve(ctx, (size_t)chunk * p.hidden * sizeof(float) + 1024, 1);
+    int rc = kp_ws_reserve(ctx, fp32_bytes > 2 * half + 2048 ? fp32_bytes : 2 * half + 2048, 1);
     if (rc != KP_OK) return rc;
-    scratch = reinterpret_cast<float*>(ctx->ws_arena[1]);
+    scratch = ctx->ws_arena[1];
   }
   for (int q0 = 0; q0 < Q; q0 += chunk) {
     const int n = (Q - q0 < chunk) ? Q - q0 : chunk;
+    const bool split = kp_conve_fc_umma(ctx, n);
     ConvK c = p;
     c.Q = n;
     c.lhs_ids = lhs_ids ? lhs_ids + (size_t)q0 * stride : nullptr;
@@ -244,13 +297,20 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
     c.mimic_index = mimic_index ? mimic_index + q0 : nullptr;
     c.drop_ids = drop_ids ? drop_ids + q0 : nullptr;
     c.x_out = x_out + (size_t)q0 * p.D;
-    c.feat_out = feat_out ? feat_out + (size_t)q0 * p.hidden : scratch;
+    c.feat_out = reinterpret_cast<float*>(scratch);
+    c.hi_out = c.lo_out = nullptr;
+    c.kpad = kp_conve_feat_kpad(ctx);
+    if (split) {
+      c.hi_out = reinterpret_cast<__nv_bfloat16*>(scratch);
+      c.lo_out = reinterpret_cast<__nv_bfloat16*>(scratch + kp_conve_feat_half_bytes(ctx, n));
+    }
     {
       KpTimer timer(ctx, kp_ctx::T_CONV, st);
       conve_conv_kernel<<<n, CV_CONV_THREADS, ((size_t)40 * p.H + 12 * p.F) * sizeof(float), st>>>(c);
     }
     KP_LAUNCHED(ctx, 1);
-    int rc = kp_conve_fc(ctx, true, n, c.feat_out, c.x_out, feat_out ? 0 : (size_t)chunk * p.hidden * sizeof(float) + 1024, st);
+    int rc = split ? kp_gemm_umma_split(ctx, c.hi_out, c.lo_out, n, ctx->cv.fc_fwd, c.x_out, p.D, st)
+                   : kp_conve_fc(ctx, true, n, c.feat_out, c.x_out, feat_out ? 0 : fp32_bytes, st);
     if (rc != KP_OK) return rc;
     conve_head_kernel<<<(int)(((size_t)n * p.D + 255) / 256), 256, 0, st>>>(c);
     KP_LAUNCHED(ctx, 1);

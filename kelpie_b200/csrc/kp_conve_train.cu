@@ -16,6 +16,7 @@
 // recomputed every step as well (the reference pushes every pair through the network with
 // fresh masks each step).
 #include "kp_flash.cuh"
+#include <cuda_bf16.h>
 #include "kp_internal.h"
 #include "kp_plan.cuh"
 #include "kp_dropout.cuh"
@@ -93,7 +94,9 @@ __global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
 struct CvBack {
   int GA, D, H, F, hidden;
   const float *conv_w, *bn1, *bn2;
-  const float* feat;   // [GA, hidden] post-ReLU (and post-dropout) feature maps saved by the forward kernel
+  const float* feat;   // [GA, hidden] post-ReLU (and post-dropout) feature maps saved by the forward kernel, or
+  const __nv_bfloat16* feat_hi;  // their bf16 heads [GA, kpad] (the forward GEMM's operand): only the sign of the maps is used
+  int kpad;
   const float* dfeat;  // [GA, hidden] = dh @ fc_w  (Linear^T, kp_gemm.cu)
   float* glhs;         // [GA, D] gradient w.r.t. the lhs embedding
   const int32_t* pair; // [GA] pair ids keying the dropout masks
@@ -126,13 +129,22 @@ __global__ void __launch_bounds__(CT) cv_backward(const CvBack p) {
   __syncthreads();
   const float4* feat4 = reinterpret_cast<const float4*>(p.feat + (size_t)g * hidden);
   const float4* dfeat4 = reinterpret_cast<const float4*>(p.dfeat + (size_t)g * hidden);
+  const uint2* hi4 = reinterpret_cast<const uint2*>(p.feat_hi + (size_t)g * p.kpad);
   for (int i4 = tid; i4 < hidden / 4; i4 += CT) {  // per_f = 38 * W2 is even, hidden a multiple of 4: a float4 may straddle two filters
-    const float4 f = feat4[i4], d = dfeat4[i4];
-    const float fv[4] = {f.x, f.y, f.z, f.w}, dv[4] = {d.x, d.y, d.z, d.w};
+    const float4 d = dfeat4[i4];
+    const float dv[4] = {d.x, d.y, d.z, d.w};
+    bool on[4];
+    if (p.feat_hi) {  // maps are >= 0: positive <=> a non-zero bf16 head
+      const uint2 h = hi4[i4];
+      on[0] = (h.x & 0x7fffu) != 0; on[1] = (h.x & 0x7fff0000u) != 0; on[2] = (h.y & 0x7fffu) != 0; on[3] = (h.y & 0x7fff0000u) != 0;
+    } else {
+      const float4 f = feat4[i4];
+      on[0] = f.x > 0.f; on[1] = f.y > 0.f; on[2] = f.z > 0.f; on[3] = f.w > 0.f;
+    }
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = i4 * 4 + j, c = i / per_f;
-      dcv[c * stride + (i - c * per_f)] = fv[j] > 0.f ? dv[j] * a2s[c] : 0.f;  // dropped channels have feat == 0
+      dcv[c * stride + (i - c * per_f)] = on[j] ? dv[j] * a2s[c] : 0.f;  // dropped channels have feat == 0
     }
   }
   __syncthreads();
@@ -184,7 +196,8 @@ __global__ void __launch_bounds__(CT) cv_backward_generic(const CvBack p) {
   for (int i = tid; i < hidden; i += CT) {
     const int c = i / per_f;
     const float a2 = p.bn2[c] / sqrtf(p.bn2[3 * p.F + c] + 1e-5f);
-    const bool on = p.feat[(size_t)g * hidden + i] > 0.f;  // dropped channels are 0
+    const bool on = p.feat_hi ? (__bfloat16_as_ushort(p.feat_hi[(size_t)g * p.kpad + i]) & 0x7fffu) != 0
+                              : p.feat[(size_t)g * hidden + i] > 0.f;  // dropped channels are 0
     float d = on ? p.dfeat[(size_t)g * hidden + i] * a2 : 0.f;
     if (on && p.p_fm > 0.f) d *= kp_drop_scale(p.seed, p.pair[g], p.step, KP_DROP_FEATURE + c, p.p_fm);
     dcv[i] = d;
@@ -281,9 +294,12 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   const int G = (int)cap, Gpad = ((G + 63) / 64) * 64;
   const size_t SG = kp_flash_part_rows(ctx, G);  // rows of strip partials, worst case over steps of <= G rows
 
+  // feature maps of a step's pairs, kept for the backward pass: fp32 [G, hidden], or the forward GEMM's split operand (kp_conve_fc_umma)
+  size_t feat_bytes = (size_t)G * hidden * 4;
+  if (kp_conve_fc_umma(ctx, G) && 2 * kp_conve_feat_half_bytes(ctx, G) > feat_bytes) feat_bytes = 2 * kp_conve_feat_half_bytes(ctx, G);
   size_t need = 3 * WsCursor::need((size_t)C * D, 4) + 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8) +
                 7 * WsCursor::need(G, 4) + 2 * WsCursor::need((size_t)Gpad * D, 4) +
-                2 * WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
+                WsCursor::need(feat_bytes, 1) + WsCursor::need((size_t)G * hidden, 4) + 2 * WsCursor::need((size_t)G * D, 4) + WsCursor::need(G, 4) +
                 2 * WsCursor::need(SG, 4) + WsCursor::need(SG * D, 4);
   int rc = kp_ws_reserve(ctx, need);
   if (rc != KP_OK) return rc;
@@ -300,7 +316,7 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
   pl.b_cand = ws.take<int32_t>(G); pl.b_lhs = ws.take<int32_t>(G); pl.b_rel = ws.take<int32_t>(G); pl.b_row = ws.take<int32_t>(G);
   float* xA = ws.take<float>((size_t)Gpad * D);
   float* xB = ws.take<float>((size_t)Gpad * D);
-  float* feat = ws.take<float>((size_t)G * hidden);
+  float* feat = reinterpret_cast<float*>(ws.take<char>(feat_bytes));
   float* dfeat = ws.take<float>((size_t)G * hidden);
   float* dh = ws.take<float>((size_t)G * D);
   float* glhs = ws.take<float>((size_t)G * D);
@@ -362,6 +378,8 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
       k.GA = (int)GA; k.D = D; k.H = ctx->cv.H; k.F = ctx->cv.n_filters; k.hidden = hidden;
       k.conv_w = ctx->cv.conv_w; k.bn1 = ctx->cv.bn1; k.bn2 = ctx->cv.bn2;
       k.feat = feat; k.dfeat = dfeat; k.glhs = glhs;
+      k.feat_hi = kp_conve_fc_umma(ctx, (int)GA) ? reinterpret_cast<const __nv_bfloat16*>(feat) : nullptr;
+      k.kpad = kp_conve_feat_kpad(ctx);
       k.pair = pl.a_truth; k.seed = seed; k.step = (int)t; k.p_in = ctx->cv.drop_in; k.p_fm = ctx->cv.drop_fm;
       KP_LAUNCHED(ctx, 1);
       if ((rc = kp_conve_fc(ctx, false, (int)GA, dh, dfeat, 0, st)) != KP_OK) return rc;

@@ -410,13 +410,16 @@ int kp_umma_b_prepare(kp_ctx* ctx, const float* B, int N, int K, bool transpose,
   return KP_OK;
 }
 
+size_t kp_gemm_umma_a_bytes(int M, const kp_umma_b& B) {  // bytes of ONE split half (hi or lo) of an A operand of M rows
+  const long long Mpad = (long long)((M + 255) / 256) * 256;
+  return ((size_t)Mpad * B.Kpad * 2 + 1023) & ~size_t(1023);
+}
+
 int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umma_b& B, float* C, long long ldc, size_t ws_offset,
                  cudaStream_t st) {
   if (M <= 0) return KP_OK;
-  if (B.N % 4 != 0 || ldc % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "tcgen05 GEMM needs N and ldc multiple of 4");
-  const int n_mt = ((M + 255) / 256) * 2;
-  const long long Mpad = (long long)n_mt * 128;
-  const size_t abytes = ((size_t)Mpad * B.Kpad * 2 + 1023) & ~size_t(1023);
+  const long long Mpad = (long long)((M + 255) / 256) * 256;
+  const size_t abytes = kp_gemm_umma_a_bytes(M, B);
   int rc;
   ws_offset = (ws_offset + 1023) & ~size_t(1023);  // the caller's own scratch at the start of arena 1 (may hold A itself)
   if ((rc = kp_ws_reserve(ctx, ws_offset + 2 * abytes + 2048, 1)) != KP_OK) return rc;
@@ -424,9 +427,20 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
   __nv_bfloat16* al = reinterpret_cast<__nv_bfloat16*>(ctx->ws_arena[1] + ws_offset + abytes);
   split2_kernel<<<ctx->sm_count * 8, 256, 0, st>>>(A, M, B.K, lda, Mpad, B.Kpad, ah, al);
   KP_LAUNCHED(ctx, 1);
+  return kp_gemm_umma_split(ctx, ah, al, M, B, C, ldc, st);
+}
+
+// The same with A already split by its producer: bf16 hi / lo [M rounded up to 256, B.Kpad], columns K..Kpad zero (rows beyond M
+// are read but their results are not stored).
+int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const kp_umma_b& B, float* C, long long ldc, cudaStream_t st) {
+  if (M <= 0) return KP_OK;
+  if (B.N % 4 != 0 || ldc % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "tcgen05 GEMM needs N and ldc multiple of 4");
+  const int n_mt = ((M + 255) / 256) * 2;
+  const long long Mpad = (long long)n_mt * 128;
+  int rc;
   CUtensorMap ah_map, al_map;
-  if ((rc = kp_encode_2d(ctx, &ah_map, ah, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, B.Kpad, B.Kpad, 128, 64, true)) != KP_OK) return rc;
-  if ((rc = kp_encode_2d(ctx, &al_map, al, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, B.Kpad, B.Kpad, 128, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &ah_map, const_cast<void*>(ah), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, B.Kpad, B.Kpad, 128, 64, true)) != KP_OK) return rc;
+  if ((rc = kp_encode_2d(ctx, &al_map, const_cast<void*>(al), CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Mpad, B.Kpad, B.Kpad, 128, 64, true)) != KP_OK) return rc;
   GK_ p;
   p.M = M;
   p.N = B.N;

@@ -88,6 +88,7 @@ struct kp_ctx {
                                // to move post-trained rows by 1e-3 (measured: the same candidate in batches of 2 / 64 / 300 / 1200).
                                // 256 tiles = 2048 K-steps bound it at 1.2e-4 of O; the strips are merged in fp32 (round to nearest).
   int64_t umma_qres = 1;  // pair kernel (rows of <= 256 floats): query tile resident in shared memory (kp_flash_umma2.cu)
+  int64_t conv_split = 1;  // ConvE conv kernel emits the Linear GEMM's bf16 hi / lo operand directly (kp_conve.cu)
   int64_t gemm_wide = 1;  // ConvE Linear layer GEMMs with accumulator tiles of up to 256 columns (kp_gemm_umma.cu)
   int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
@@ -259,8 +260,16 @@ int kp_rank_umma_launch(kp_ctx* ctx, const kp_pass_args& a, cudaStream_t st);
 int kp_umma_b_prepare(kp_ctx* ctx, const float* B, int N, int K, bool transpose, kp_umma_b* out, cudaStream_t st);
 int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umma_b& B, float* C, long long ldc, size_t ws_offset,
                  cudaStream_t st);
+size_t kp_gemm_umma_a_bytes(int M, const kp_umma_b& B);
+int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const kp_umma_b& B, float* C, long long ldc, cudaStream_t st);
 // ConvE Linear layer: forward (x = feat W^T) / backward (dfeat = dh W); tcgen05 from 128 rows on, else CUDA cores
 int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st);
+// Whether the forward Linear layer of M pairs runs on tcgen05: the conv kernel then writes the feature maps as the GEMM's split
+// A operand -- bf16 hi [M rounded up to 256, Kpad] at the start of `feat_out`, lo kp_conve_feat_half_bytes() behind it -- instead
+// of fp32 [M, hidden] followed by a separate split pass.
+bool kp_conve_fc_umma(const kp_ctx* ctx, int M);
+size_t kp_conve_feat_half_bytes(const kp_ctx* ctx, int M);
+int kp_conve_feat_kpad(const kp_ctx* ctx);
 
 // Strip count for a launch of `units` co-resident CTA groups per strip on `slots` group slots: the entity (or
 // column) range is cut into s strips so that units * s fills whole waves.  Less than a wave per strip: up to

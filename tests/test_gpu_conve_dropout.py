@@ -107,3 +107,33 @@ def test_conve_dropout_matches_torch_with_same_masks(rates):
     # and the masks matter: a different seed gives different rows
     other = ctx.post_train(runtime.make_hp("ConvE", hp), dropout_seed=seed + 1, **arrs).cpu().numpy()
     assert np.abs(other - got).max() > 1e-6
+
+
+@pytest.mark.parametrize("rates", [(0.0, 0.0, 0.0), (0.1, 0.25, 0.3)])
+def test_conv_kernel_split_output_is_the_split_pass(rates):
+    """>= 128 pairs per step: the Linear layer runs on tcgen05 and the conv kernel writes its bf16 hi / lo operand itself
+    (kp_conve.cu); the rows must be those of the fp32 feature maps followed by the separate split pass, bit for bit,
+    and stay within 1e-4 of the CUDA-core Linear layer."""
+    from kelpie_b200 import plans, runtime
+    z, meta, kg, w, order = load("ConvE")
+    N, R, D = kg.num_entities, kg.num_relations, w.dim
+    conve = dict(w.conve)
+    conve["dropout"] = rates
+    hp = dict(meta["hp"], batch_size=8, epochs=3)
+    rng = np.random.default_rng(5)
+    b = plans.Batch("ConvE", N, R, hp)
+    for _ in range(70):  # ~ 70 * 6 pairs per step, both directions
+        T = int(rng.integers(4, 9))
+        facts = [((N, int(rng.integers(0, R)), int(rng.integers(0, N))) if rng.random() < 0.5
+                  else (int(rng.integers(0, N)), int(rng.integers(0, R)), N)) for _ in range(T)]
+        b.add(facts, rng.random(D).astype(np.float32))
+    arrs = b.arrays()
+    rows = {}
+    for name, opts in (("split", {}), ("fp32", {"conv_split": 0}), ("simt", {"umma_fc": 0})):
+        ctx = runtime.Context("ConvE", z["w_ent"], z["w_rel"], conve=conve)
+        for k, v in opts.items():
+            ctx.set_option(k, v)
+        rows[name] = ctx.post_train(runtime.make_hp("ConvE", hp), dropout_seed=99, **arrs).cpu().numpy()
+    assert np.isfinite(rows["split"]).all()
+    assert np.array_equal(rows["split"], rows["fp32"])
+    assert np.abs(rows["split"] - rows["simt"]).max() <= 1e-4 * np.abs(rows["simt"]).max()
