@@ -98,29 +98,47 @@ __global__ void __launch_bounds__(CV_CONV_THREADS) conve_conv_kernel(const ConvK
     if (p.hi_out) {  // a lane owns two neighbouring positions: one 4-byte store per filter and half (hi = bf16(x), lo = bf16(x - hi))
       uint32_t* hi = reinterpret_cast<uint32_t*>(p.hi_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
       uint32_t* lo = reinterpret_cast<uint32_t*>(p.lo_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
+      const bool even = (H & 1) == 0;  // both positions of a lane then sit in one image row: its 3 x 4 window as six 8-byte loads
       for (int pp = lane; pp < per_f / 2; pp += 32) {  // per_f = 38 * W2 is even
         const int pos = 2 * pp, y0 = pos / W2, y1 = (pos + 1) / W2;
         const float* tap0 = img + pos + 2 * y0;
         const float* tap1 = img + pos + 1 + 2 * y1;
         float acc0[4] = {bias[0], bias[1], bias[2], bias[3]}, acc1[4] = {bias[0], bias[1], bias[2], bias[3]};
+        if (even) {
+          const float2* t2 = reinterpret_cast<const float2*>(tap0);
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy)
+          for (int dy = 0; dy < 3; ++dy) {
+            const float2 a = t2[dy * (H >> 1)], b = t2[dy * (H >> 1) + 1];
+            const float v[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
-          for (int dx = 0; dx < 3; ++dx) {
-            const float v0 = tap0[dy * H + dx], v1 = tap1[dy * H + dx];
+            for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-            for (int f = 0; f < 4; ++f) {
-              acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v0, acc0[f]);
-              acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v1, acc1[f]);
-            }
+              for (int f = 0; f < 4; ++f) {
+                acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v[dx], acc0[f]);
+                acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v[dx + 1], acc1[f]);
+              }
           }
+        } else {
+#pragma unroll
+          for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+            for (int dx = 0; dx < 3; ++dx) {
+              const float v0 = tap0[dy * H + dx], v1 = tap1[dy * H + dx];
+#pragma unroll
+              for (int f = 0; f < 4; ++f) {
+                acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v0, acc0[f]);
+                acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v1, acc1[f]);
+              }
+            }
+        }
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
           const float x0 = fmaxf(__fmaf_rn(acc0[f], a2[f], b2[f]), 0.f), x1 = fmaxf(__fmaf_rn(acc1[f], a2[f], b2[f]), 0.f);
-          const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-          hi[(size_t)f * (per_f / 2) + pp] = pack_bf16x2(h0, h1);
-          lo[(size_t)f * (per_f / 2) + pp] =
-              pack_bf16x2(__float2bfloat16_rn(x0 - __bfloat162float(h0)), __float2bfloat16_rn(x1 - __bfloat162float(h1)));
+          const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x (low half) = x0
+          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+          const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
+          hi[(size_t)f * (per_f / 2) + pp] = hb;
+          lo[(size_t)f * (per_f / 2) + pp] = *reinterpret_cast<const uint32_t*>(&l);
         }
       }
       continue;

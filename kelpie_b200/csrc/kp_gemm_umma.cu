@@ -24,7 +24,9 @@ struct GCtl {
   uint64_t s_full[2], s_free[2];
   uint32_t tmem_base;
 };
-constexpr size_t G_SMEM = (size_t)NSLOT * SLOT + sizeof(GCtl) + 1024;
+constexpr int STAGE = 4096;  // per epilogue warp: 32 rows x 32 columns of C on their way from TMEM to row-contiguous global stores
+constexpr size_t G_SMEM = (size_t)NSLOT * SLOT + 4 * STAGE + sizeof(GCtl) + 1024;
+static_assert(G_SMEM <= 232448, "shared memory budget of one CTA");
 
 struct GK_ {
   int M, N, KB, ksteps, n_tiles, tiles_per_strip, kb_per_split;  // kb_per_split > 0: split-K over blockIdx.z, C accumulated with reductions
@@ -56,7 +58,8 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
   extern __shared__ uint8_t graw[];
   uint8_t* sm = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(graw) + 1023) & ~uintptr_t(1023));
   uint8_t* ring = sm;
-  GCtl* ctl = reinterpret_cast<GCtl*>(sm + (size_t)NSLOT * SLOT);
+  uint8_t* stage = sm + (size_t)NSLOT * SLOT;
+  GCtl* ctl = reinterpret_cast<GCtl*>(stage + 4 * STAGE);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int strip = blockIdx.y, mtile = blockIdx.x;
@@ -171,10 +174,14 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
       }
     }
   } else {
+    // A thread reads one row of the accumulator from TMEM; the warp's 32 x 32 block goes through shared memory (16-byte chunks
+    // XOR-swizzled by the row: conflict-free both ways) so that every store instruction writes 4 rows x 128 contiguous bytes of C
+    // instead of 16 bytes in each of 32 rows.
     const int sub = warp & 3;
-    const int row = sub * 32 + lane;
     const uint32_t lane_off = (uint32_t)(sub * 32) << 16;
-    const long long m = (long long)mtile * 128 + row;
+    const long long m0 = (long long)mtile * 128 + sub * 32;
+    float4* st4 = reinterpret_cast<float4*>(stage + (size_t)sub * STAGE);
+    const int rr = lane >> 3, cc = lane & 7;
     const uint32_t s_free_leader0 = ptx::mapa_u32(ptx::smem_u32(&ctl->s_free[0]), 0);
     for (int i = 0; i < ntile; ++i) {
       const int sb = i & 1;
@@ -187,20 +194,25 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
         uint32_t r[32];
         ptx::tmem_ld_32x32(s_addr + c0, r);
         ptx::tmem_ld_wait();
-        if (m < p.M) {
-          float* dst = p.C + m * p.ldc + n0 + c0;
 #pragma unroll
-          for (int c = 0; c < 32; c += 4)
-            if (n0 + c0 + c < p.N) {
-              if (p.kb_per_split > 0)
-                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + c), "f"(__uint_as_float(r[c])),
-                             "f"(__uint_as_float(r[c + 1])), "f"(__uint_as_float(r[c + 2])), "f"(__uint_as_float(r[c + 3]))
-                             : "memory");
-              else
-                *reinterpret_cast<float4*>(dst + c) =
-                    make_float4(__uint_as_float(r[c]), __uint_as_float(r[c + 1]), __uint_as_float(r[c + 2]), __uint_as_float(r[c + 3]));
-            }
+        for (int c = 0; c < 8; ++c)
+          st4[lane * 8 + (c ^ (lane & 7))] = make_float4(__uint_as_float(r[4 * c]), __uint_as_float(r[4 * c + 1]),
+                                                          __uint_as_float(r[4 * c + 2]), __uint_as_float(r[4 * c + 3]));
+        __syncwarp();
+        const int col = n0 + c0 + cc * 4;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int R = it * 4 + rr;
+          const float4 v = st4[R * 8 + (cc ^ (R & 7))];
+          if (m0 + R < p.M && col < p.N) {
+            float* dst = p.C + (m0 + R) * p.ldc + col;
+            if (p.kb_per_split > 0)
+              asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            else
+              *reinterpret_cast<float4*>(dst) = v;
+          }
         }
+        __syncwarp();
       }
       ptx::tc_fence_before();
       ptx::mbar_arrive_cluster(s_free_leader0 + 8u * sb);
