@@ -5,6 +5,7 @@
 #include "kp_internal.h"
 #include "kp_ptx.cuh"
 #include "kp_dropout.cuh"
+#include "kp_conve_head.cuh"
 
 #include <cuda_bf16.h>
 
@@ -35,136 +36,145 @@ struct ConvK {
   float p_in, p_fm, p_hid;
 };
 
-__device__ __forceinline__ void bn_affine(const float* bn, int n, int i, float& alpha, float& beta) {
-  // bn = {weight[n], bias[n], mean[n], var[n]}
-  const float inv = 1.f / sqrtf(bn[3 * n + i] + 1e-5f);
-  alpha = bn[i] * inv;
-  beta = bn[n + i] - bn[2 * n + i] * alpha;
-}
 
-// Stage 1 (one CTA per pair): stacked image -> BN1 (+input dropout) -> Conv 3x3 -> BN2 -> ReLU
-// (+Dropout2d) -> feat[q, hidden].
-// A warp owns a group of 4 filters (their 36 weights and BN2 affines sit in registers) and its lanes sweep the 38 x W2
-// output positions: every image tap read from shared memory feeds 4 FMAs and every store instruction of the warp
-// writes 32 consecutive floats of one filter's plane.
+// Stage 1: stacked image -> BN1 (+input dropout) -> Conv 3x3 -> BN2 -> ReLU (+Dropout2d) -> feat[q, hidden].
+// Persistent CTAs walk the pairs (grid stride): the filter weights and BN2 affines are staged once per CTA and -- with 32 filters,
+// one group of 4 per warp -- stay in registers over all of a CTA's pairs; the image is double-buffered in shared memory (one
+// barrier per pair).  A warp owns a group of 4 filters and its lanes sweep the 38 x W2 output positions: every image tap read
+// from shared memory feeds 4 (split output: 8) FMAs and every store instruction of the warp writes 128 consecutive bytes of one
+// filter's plane.
 constexpr int CV_CONV_THREADS = 256;
-__global__ void __launch_bounds__(CV_CONV_THREADS) conve_conv_kernel(const ConvK p) {
+__global__ void __launch_bounds__(CV_CONV_THREADS, 3) conve_conv_kernel(const ConvK p) {
   extern __shared__ float sm[];
   const int H = p.H, W2 = H - 2, D = p.D, F = p.F;
   const int img_sz = 40 * H;
-  float* img = sm;            // [40*H]
-  float* wsm = img + img_sz;  // [9F] weights | [F] bias | [F] alpha2 | [F] beta2
+  float* imgs = sm;               // [2][40*H]
+  float* wsm = imgs + 2 * img_sz;  // [9F] weights | [F] bias | [F] alpha2 | [F] beta2
   float* bsm = wsm + 9 * F;
   float* a2s = bsm + F;
   float* b2s = a2s + F;
-  const int tid = threadIdx.x, q = blockIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   float a1, b1;
   bn_affine(p.bn1, 1, 0, a1, b1);
-  const int s = p.lhs_ids ? p.lhs_ids[(size_t)q * p.stride] : p.N, r = p.rel_ids[(size_t)q * p.stride];
-  const float* l = (s == p.N) ? p.mimic + (size_t)(p.mimic_index ? p.mimic_index[q] : q) * D : p.ent + (size_t)s * D;
   const bool drop = p.drop_ids != nullptr;
-  const int pid = drop ? p.drop_ids[q] : 0;
-  for (int k = tid; k < img_sz; k += CV_CONV_THREADS) {
-    float v = (k < D) ? l[k] : p.rel[(size_t)r * D + (k - D)];
-    v = v * a1 + b1;
-    if (drop && p.p_in > 0.f) v *= kp_drop_scale(p.seed, pid, p.step, KP_DROP_INPUT + k, p.p_in);
-    img[k] = v;
-  }
   for (int k = tid; k < 9 * F; k += CV_CONV_THREADS) wsm[k] = p.conv_w[k];
   for (int c = tid; c < F; c += CV_CONV_THREADS) {
     float a2, b2;
     bn_affine(p.bn2, F, c, a2, b2);
-    if (drop && p.p_fm > 0.f) {  // Dropout2d scales a whole channel; relu(a x + b) * s = relu(s a x + s b) for s >= 0
-      const float sc = kp_drop_scale(p.seed, pid, p.step, KP_DROP_FEATURE + c, p.p_fm);
-      a2 *= sc;
-      b2 *= sc;
-    }
     bsm[c] = p.conv_b[c];
     a2s[c] = a2;
     b2s[c] = b2;
   }
-  __syncthreads();
   const int per_f = 38 * W2;
-  for (int c0 = warp * 4; c0 < F; c0 += (CV_CONV_THREADS / 32) * 4) {
-    float w[4][9], bias[4], a2[4], b2[4];
-#pragma unroll
-    for (int f = 0; f < 4; ++f) {
-#pragma unroll
-      for (int k = 0; k < 9; ++k) w[f][k] = wsm[(c0 + f) * 9 + k];
-      bias[f] = bsm[c0 + f];
-      a2[f] = a2s[c0 + f];
-      b2[f] = b2s[c0 + f];
+  const bool even = (H & 1) == 0;  // split output: both positions of a lane then sit in one image row (3 x 4 window, six 8-byte loads)
+  float w[4][9], bias[4], a2b[4], b2b[4];
+  int c0_regs = -1;
+  int it = 0;
+  for (int q = blockIdx.x; q < p.Q; q += gridDim.x, ++it) {
+    float* img = imgs + (it & 1) * img_sz;
+    const int s = p.lhs_ids ? p.lhs_ids[(size_t)q * p.stride] : p.N, r = p.rel_ids[(size_t)q * p.stride];
+    const float* l = (s == p.N) ? p.mimic + (size_t)(p.mimic_index ? p.mimic_index[q] : q) * D : p.ent + (size_t)s * D;
+    const int pid = drop ? p.drop_ids[q] : 0;
+    for (int k = tid; k < img_sz; k += CV_CONV_THREADS) {
+      float v = (k < D) ? l[k] : p.rel[(size_t)r * D + (k - D)];
+      v = v * a1 + b1;
+      if (drop && p.p_in > 0.f) v *= kp_drop_scale(p.seed, pid, p.step, KP_DROP_INPUT + k, p.p_in);
+      img[k] = v;
     }
-    if (p.hi_out) {  // a lane owns two neighbouring positions: one 4-byte store per filter and half (hi = bf16(x), lo = bf16(x - hi))
-      uint32_t* hi = reinterpret_cast<uint32_t*>(p.hi_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
-      uint32_t* lo = reinterpret_cast<uint32_t*>(p.lo_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
-      const bool even = (H & 1) == 0;  // both positions of a lane then sit in one image row: its 3 x 4 window as six 8-byte loads
-      for (int pp = lane; pp < per_f / 2; pp += 32) {  // per_f = 38 * W2 is even
-        const int pos = 2 * pp, y0 = pos / W2, y1 = (pos + 1) / W2;
-        const float* tap0 = img + pos + 2 * y0;
-        const float* tap1 = img + pos + 1 + 2 * y1;
-        float acc0[4] = {bias[0], bias[1], bias[2], bias[3]}, acc1[4] = {bias[0], bias[1], bias[2], bias[3]};
-        if (even) {
-          const float2* t2 = reinterpret_cast<const float2*>(tap0);
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy) {
-            const float2 a = t2[dy * (H >> 1)], b = t2[dy * (H >> 1) + 1];
-            const float v[4] = {a.x, a.y, b.x, b.y};
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx)
-#pragma unroll
-              for (int f = 0; f < 4; ++f) {
-                acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v[dx], acc0[f]);
-                acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v[dx + 1], acc1[f]);
-              }
-          }
-        } else {
-#pragma unroll
-          for (int dy = 0; dy < 3; ++dy)
-#pragma unroll
-            for (int dx = 0; dx < 3; ++dx) {
-              const float v0 = tap0[dy * H + dx], v1 = tap1[dy * H + dx];
-#pragma unroll
-              for (int f = 0; f < 4; ++f) {
-                acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v0, acc0[f]);
-                acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v1, acc1[f]);
-              }
-            }
-        }
+    __syncthreads();  // the image of this pair (and, first time, the weights); the other buffer is free once every thread got here
+    for (int c0 = warp * 4; c0 < F; c0 += (CV_CONV_THREADS / 32) * 4) {
+      if (c0 != c0_regs) {
 #pragma unroll
         for (int f = 0; f < 4; ++f) {
-          const float x0 = fmaxf(__fmaf_rn(acc0[f], a2[f], b2[f]), 0.f), x1 = fmaxf(__fmaf_rn(acc1[f], a2[f], b2[f]), 0.f);
-          const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x (low half) = x0
-          const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
-          const __nv_bfloat162 l = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
-          hi[(size_t)f * (per_f / 2) + pp] = hb;
-          lo[(size_t)f * (per_f / 2) + pp] = *reinterpret_cast<const uint32_t*>(&l);
+#pragma unroll
+          for (int k = 0; k < 9; ++k) w[f][k] = wsm[(c0 + f) * 9 + k];
+          bias[f] = bsm[c0 + f];
+          a2b[f] = a2s[c0 + f];
+          b2b[f] = b2s[c0 + f];
+        }
+        c0_regs = c0;
+      }
+      float a2[4], b2[4];
+#pragma unroll
+      for (int f = 0; f < 4; ++f) {
+        a2[f] = a2b[f];
+        b2[f] = b2b[f];
+        if (drop && p.p_fm > 0.f) {  // Dropout2d scales a whole channel; relu(a x + b) * s = relu(s a x + s b) for s >= 0
+          const float sc = kp_drop_scale(p.seed, pid, p.step, KP_DROP_FEATURE + c0 + f, p.p_fm);
+          a2[f] *= sc;
+          b2[f] *= sc;
         }
       }
-      continue;
-    }
-    float* out = p.feat_out + (size_t)q * p.hidden + (size_t)c0 * per_f;
-    for (int pos = lane; pos < per_f; pos += 32) {
-      const int y = pos / W2;
-      const float* tap = img + pos + 2 * y;  // y * H + x with H = W2 + 2
-      float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
+      if (p.hi_out) {  // a lane owns two neighbouring positions: one 4-byte store per filter and half (hi = bf16(x), lo = bf16(x - hi))
+        uint32_t* hi = reinterpret_cast<uint32_t*>(p.hi_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
+        uint32_t* lo = reinterpret_cast<uint32_t*>(p.lo_out + (size_t)q * p.kpad + (size_t)c0 * per_f);
+        for (int pp = lane; pp < per_f / 2; pp += 32) {  // per_f = 38 * W2 is even
+          const int pos = 2 * pp, y0 = pos / W2, y1 = (pos + 1) / W2;
+          const float* tap0 = img + pos + 2 * y0;
+          const float* tap1 = img + pos + 1 + 2 * y1;
+          float acc0[4] = {bias[0], bias[1], bias[2], bias[3]}, acc1[4] = {bias[0], bias[1], bias[2], bias[3]};
+          if (even) {
+            const float2* t2 = reinterpret_cast<const float2*>(tap0);
 #pragma unroll
-      for (int dy = 0; dy < 3; ++dy)
+            for (int dy = 0; dy < 3; ++dy) {
+              const float2 a = t2[dy * (H >> 1)], b = t2[dy * (H >> 1) + 1];
+              const float v[4] = {a.x, a.y, b.x, b.y};
 #pragma unroll
-        for (int dx = 0; dx < 3; ++dx) {
-          const float v = tap[dy * H + dx];
+              for (int dx = 0; dx < 3; ++dx)
 #pragma unroll
-          for (int f = 0; f < 4; ++f) acc[f] = __fmaf_rn(w[f][dy * 3 + dx], v, acc[f]);
+                for (int f = 0; f < 4; ++f) {
+                  acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v[dx], acc0[f]);
+                  acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v[dx + 1], acc1[f]);
+                }
+            }
+          } else {
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+              for (int dx = 0; dx < 3; ++dx) {
+                const float v0 = tap0[dy * H + dx], v1 = tap1[dy * H + dx];
+#pragma unroll
+                for (int f = 0; f < 4; ++f) {
+                  acc0[f] = __fmaf_rn(w[f][dy * 3 + dx], v0, acc0[f]);
+                  acc1[f] = __fmaf_rn(w[f][dy * 3 + dx], v1, acc1[f]);
+                }
+              }
+          }
+#pragma unroll
+          for (int f = 0; f < 4; ++f) {
+            const float x0 = fmaxf(__fmaf_rn(acc0[f], a2[f], b2[f]), 0.f), x1 = fmaxf(__fmaf_rn(acc1[f], a2[f], b2[f]), 0.f);
+            const __nv_bfloat162 h = __floats2bfloat162_rn(x0, x1);  // .x (low half) = x0
+            const uint32_t hb = *reinterpret_cast<const uint32_t*>(&h);
+            const __nv_bfloat162 lw = __floats2bfloat162_rn(x0 - __uint_as_float(hb << 16), x1 - __uint_as_float(hb & 0xffff0000u));
+            hi[(size_t)f * (per_f / 2) + pp] = hb;
+            lo[(size_t)f * (per_f / 2) + pp] = *reinterpret_cast<const uint32_t*>(&lw);
+          }
         }
+        continue;
+      }
+      float* out = p.feat_out + (size_t)q * p.hidden + (size_t)c0 * per_f;
+      for (int pos = lane; pos < per_f; pos += 32) {
+        const int y = pos / W2;
+        const float* tap = img + pos + 2 * y;  // y * H + x with H = W2 + 2
+        float acc[4] = {bias[0], bias[1], bias[2], bias[3]};
 #pragma unroll
-      for (int f = 0; f < 4; ++f) out[(size_t)f * per_f + pos] = fmaxf(__fmaf_rn(acc[f], a2[f], b2[f]), 0.f);
+        for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+          for (int dx = 0; dx < 3; ++dx) {
+            const float v = tap[dy * H + dx];
+#pragma unroll
+            for (int f = 0; f < 4; ++f) acc[f] = __fmaf_rn(w[f][dy * 3 + dx], v, acc[f]);
+          }
+#pragma unroll
+        for (int f = 0; f < 4; ++f) out[(size_t)f * per_f + pos] = fmaxf(__fmaf_rn(acc[f], a2[f], b2[f]), 0.f);
+      }
     }
+    if (p.hi_out)  // zero columns up to the GEMM's k-block boundary
+      for (int k = p.hidden + tid; k < p.kpad; k += CV_CONV_THREADS) {
+        p.hi_out[(size_t)q * p.kpad + k] = __float2bfloat16_rn(0.f);
+        p.lo_out[(size_t)q * p.kpad + k] = __float2bfloat16_rn(0.f);
+      }
   }
-  if (p.hi_out)  // zero columns up to the GEMM's k-block boundary
-    for (int k = p.hidden + tid; k < p.kpad; k += CV_CONV_THREADS) {
-      p.hi_out[(size_t)q * p.kpad + k] = __float2bfloat16_rn(0.f);
-      p.lo_out[(size_t)q * p.kpad + k] = __float2bfloat16_rn(0.f);
-    }
 }
 
 // Stage 3: x = ReLU(BN3(dropout(raw + fc_b)))   (stage 2 is the Linear GEMM, kp_gemm.cu)
@@ -172,11 +182,8 @@ __global__ void conve_head_kernel(const ConvK p) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (size_t)p.Q * p.D) return;
   const int q = (int)(i / p.D), k = (int)(i % p.D);
-  float a3, b3;
-  bn_affine(p.bn3, p.D, k, a3, b3);
-  float h = p.x_out[i] + p.fc_b[k];
-  if (p.drop_ids && p.p_hid > 0.f) h *= kp_drop_scale(p.seed, p.drop_ids[q], p.step, KP_DROP_HIDDEN + k, p.p_hid);
-  p.x_out[i] = fmaxf(h * a3 + b3, 0.f);
+  kp_conve_head hd{p.fc_b, p.bn3, p.drop_ids, p.seed, p.step, p.p_hid};
+  p.x_out[i] = kp_conve_head_apply(hd, p.D, q, k, p.x_out[i]);
 }
 
 __global__ void colsum_kernel(int N, int D, const float* __restrict__ ent, float* __restrict__ out) {
@@ -324,9 +331,12 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
     }
     {
       KpTimer timer(ctx, kp_ctx::T_CONV, st);
-      conve_conv_kernel<<<n, CV_CONV_THREADS, ((size_t)40 * p.H + 12 * p.F) * sizeof(float), st>>>(c);
+      const int grid = n < ctx->sm_count * 6 ? n : ctx->sm_count * 6;  // persistent from a few pairs per CTA on
+      conve_conv_kernel<<<grid, CV_CONV_THREADS, ((size_t)80 * p.H + 12 * p.F) * sizeof(float), st>>>(c);
     }
     KP_LAUNCHED(ctx, 1);
+    // (the head -- bias, dropout, BN3, ReLU -- stays a kernel of its own: in the GEMM's epilogue, one tile per CTA here, its
+    //  208 sqrt / divide / hash evaluations per thread are a serial tail: 175 us against 133 + 17 us)
     int rc = split ? kp_gemm_umma_split(ctx, c.hi_out, c.lo_out, n, ctx->cv.fc_fwd, c.x_out, p.D, st)
                    : kp_conve_fc(ctx, true, n, c.feat_out, c.x_out, feat_out ? 0 : fp32_bytes, st);
     if (rc != KP_OK) return rc;

@@ -205,6 +205,7 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
           const int R = it * 4 + rr;
           const float4 v = st4[R * 8 + (cc ^ (R & 7))];
           if (m0 + R < p.M && col < p.N) {
+
             float* dst = p.C + (m0 + R) * p.ldc + col;
             if (p.kb_per_split > 0)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
