@@ -56,6 +56,14 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->umma_max_tps = value;
     return KP_OK;
   }
+  if (!strcmp(name, "gemm_ksplit")) {
+    ctx->gemm_ksplit = value;
+    return KP_OK;
+  }
+  if (!strcmp(name, "umma_fc_min_rows")) {
+    ctx->umma_fc_min_rows = value < 1 ? 1 : value;
+    return KP_OK;
+  }
   if (!strcmp(name, "conv_split")) {
     ctx->conv_split = value;
     return KP_OK;

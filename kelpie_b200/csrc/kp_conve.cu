@@ -26,6 +26,8 @@ struct ConvK {
   const int32_t* mimic_index;  // row of `mimic` used by query q (NULL: row q)
   const float *conv_w, *conv_b, *fc_w, *fc_b, *bn1, *bn2, *bn3;
   float* x_out;      // [Q, D]
+  const float* parts;  // n_parts > 1: the Linear layer's output as n_parts partial sums [Q, D] each (K cut over CTAs), else in x_out
+  int n_parts;
   float* feat_out;   // [Q, hidden]: post-ReLU feature maps (kept for the backward pass), unless hi_out is set:
   __nv_bfloat16 *hi_out, *lo_out;  // the same as the Linear GEMM's split operand, bf16 [.., kpad] each (x = hi + lo + O(2^-16 x))
   int kpad;
@@ -183,7 +185,14 @@ __global__ void conve_head_kernel(const ConvK p) {
   if (i >= (size_t)p.Q * p.D) return;
   const int q = (int)(i / p.D), k = (int)(i % p.D);
   kp_conve_head hd{p.fc_b, p.bn3, p.drop_ids, p.seed, p.step, p.p_hid};
-  p.x_out[i] = kp_conve_head_apply(hd, p.D, q, k, p.x_out[i]);
+  float raw;
+  if (p.n_parts > 1) {
+    raw = p.parts[i];
+    for (int z = 1; z < p.n_parts; ++z) raw += p.parts[(size_t)z * p.Q * p.D + i];
+  } else {
+    raw = p.x_out[i];
+  }
+  p.x_out[i] = kp_conve_head_apply(hd, p.D, q, k, raw);
 }
 
 __global__ void colsum_kernel(int N, int D, const float* __restrict__ ent, float* __restrict__ out) {
@@ -252,7 +261,7 @@ int kp_conve_setup(kp_ctx* ctx, const kp_conve_weights* w) {
 }
 
 bool kp_conve_fc_umma(const kp_ctx* ctx, int M) {
-  return ctx->conv_split && ctx->umma_fc && !ctx->force_simt && ctx->cv.fc_fwd.ready && M >= 128;
+  return ctx->conv_split && ctx->umma_fc && !ctx->force_simt && ctx->cv.fc_fwd.ready && M >= ctx->umma_fc_min_rows;
 }
 size_t kp_conve_feat_half_bytes(const kp_ctx* ctx, int M) { return kp_gemm_umma_a_bytes(M, ctx->cv.fc_fwd); }
 int kp_conve_feat_kpad(const kp_ctx* ctx) { return ctx->cv.fc_fwd.Kpad; }
@@ -260,7 +269,7 @@ int kp_conve_feat_kpad(const kp_ctx* ctx) { return ctx->cv.fc_fwd.Kpad; }
 int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st) {
   const int D = ctx->D, hidden = ctx->cv.hidden;
   const kp_umma_b& B = forward ? ctx->cv.fc_fwd : ctx->cv.fc_bwd;
-  if (ctx->umma_fc && !ctx->force_simt && B.ready && M >= 128)
+  if (ctx->umma_fc && !ctx->force_simt && B.ready && M >= ctx->umma_fc_min_rows)
     return kp_gemm_umma(ctx, A, forward ? hidden : D, M, B, C, forward ? D : hidden, ws_offset, st);
   if (forward && M < 128 && ctx->skinny_fc) return kp_sgemm_skinny_nt(ctx, M, D, hidden, A, hidden, ctx->cv.fc_w, hidden, C, D, st);
   if (forward) return kp_sgemm(ctx, true, M, D, hidden, A, hidden, ctx->cv.fc_w, hidden, C, D, st);
@@ -306,11 +315,16 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
   const size_t fp32_bytes = (size_t)chunk * p.hidden * sizeof(float) + 1024;
   const size_t half = split_first ? kp_conve_feat_half_bytes(ctx, chunk) : 0;
   char* scratch = reinterpret_cast<char*>(feat_out);
-  if (!feat_out) {
-    int rc = kp_ws_reserve(ctx, fp32_bytes > 2 * half + 2048 ? fp32_bytes : 2 * half + 2048, 1);
+  // arena 1: [feature maps unless the caller keeps them | partial outputs of a Linear GEMM whose K is cut over CTAs]
+  const size_t parts_off = feat_out ? 0 : (((fp32_bytes > 2 * half + 2048 ? fp32_bytes : 2 * half + 2048) + 1023) & ~size_t(1023));
+  const int ks_first = split_first ? kp_gemm_umma_ksplit(ctx, chunk, ctx->cv.fc_fwd) : 1;
+  const size_t parts_bytes = ks_first > 1 ? (size_t)ks_first * chunk * p.D * sizeof(float) : 0;
+  if (parts_off + parts_bytes > 0) {
+    int rc = kp_ws_reserve(ctx, parts_off + parts_bytes, 1);
     if (rc != KP_OK) return rc;
-    scratch = ctx->ws_arena[1];
   }
+  if (!feat_out) scratch = ctx->ws_arena[1];
+  float* parts = ks_first > 1 ? reinterpret_cast<float*>(ctx->ws_arena[1] + parts_off) : nullptr;
   for (int q0 = 0; q0 < Q; q0 += chunk) {
     const int n = (Q - q0 < chunk) ? Q - q0 : chunk;
     const bool split = kp_conve_fc_umma(ctx, n);
@@ -324,6 +338,10 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
     c.x_out = x_out + (size_t)q0 * p.D;
     c.feat_out = reinterpret_cast<float*>(scratch);
     c.hi_out = c.lo_out = nullptr;
+    // (a last, shorter chunk has fewer rows per part and at least as many parts: only the first chunk's count is provided for)
+    const int ks = (split && parts && n == chunk) ? ks_first : 1;
+    c.parts = parts;
+    c.n_parts = ks;
     c.kpad = kp_conve_feat_kpad(ctx);
     if (split) {
       c.hi_out = reinterpret_cast<__nv_bfloat16*>(scratch);
@@ -337,7 +355,7 @@ int kp_conve_features_ex(kp_ctx* ctx, int Q, const int32_t* lhs_ids, const int32
     KP_LAUNCHED(ctx, 1);
     // (the head -- bias, dropout, BN3, ReLU -- stays a kernel of its own: in the GEMM's epilogue, one tile per CTA here, its
     //  208 sqrt / divide / hash evaluations per thread are a serial tail: 175 us against 133 + 17 us)
-    int rc = split ? kp_gemm_umma_split(ctx, c.hi_out, c.lo_out, n, ctx->cv.fc_fwd, c.x_out, p.D, st)
+    int rc = split ? kp_gemm_umma_split(ctx, c.hi_out, c.lo_out, n, ctx->cv.fc_fwd, c.x_out, p.D, st, ks > 1 ? parts : nullptr)
                    : kp_conve_fc(ctx, true, n, c.feat_out, c.x_out, feat_out ? 0 : fp32_bytes, st);
     if (rc != KP_OK) return rc;
     conve_head_kernel<<<(int)(((size_t)n * p.D + 255) / 256), 256, 0, st>>>(c);

@@ -57,7 +57,42 @@ struct CvDx {
   float p_hid;
 };
 
-// One WARP per pair (D = 200: seven elements per lane, no block-wide barriers).
+// One CTA per pair: for the few pairs of an explain-sized batch (every pair gets an SM's worth of latency hiding).
+__global__ void __launch_bounds__(CT) cv_dx_block(const CvDx p) {
+  extern __shared__ float dsm[];
+  __shared__ float red[CT / 32];
+  const int g = blockIdx.x, tid = threadIdx.x, D = p.D;
+  float* acc = dsm;  // [D]
+  const int c = p.a_cand[g];
+  const float* eM = p.mim + (size_t)c * D;
+  const float* x = p.xA + (size_t)g * D;
+  float part = 0.f;
+  for (int k = tid; k < D; k += CT) part = __fmaf_rn(x[k], eM[k], part);
+  const float zM = blk_sum(part, red);
+  const float sM = 1.f / (1.f + expf(-zM));
+  const int pair = p.a_pair[g];
+  const int64_t pb = p.pos_off[pair], pe = p.pos_off[pair + 1];
+  bool m_pos = false;
+  for (int64_t i = pb; i < pe; ++i) m_pos |= (p.pos_ids[i] == p.N);
+  const float scale = 1.f / ((float)(p.nA[c] + p.nB[c]) * (float)(p.N + 1));
+  for (int k = tid; k < D; k += CT) {
+    float o = 0.f;
+    for (int s = 0; s < p.n_strips; ++s) o += p.pO[((size_t)s * p.GA + g) * D + k];
+    float tsum = 0.f;
+    for (int64_t i = pb; i < pe; ++i) {
+      const int e = p.pos_ids[i];
+      tsum += (e == p.N) ? eM[k] : p.ent[(size_t)e * D + k];
+    }
+    const float dx = (o + sM * eM[k] - p.ta * tsum - p.tb * (p.colsum[k] + eM[k])) * scale;
+    const float a3 = p.bn3[k] / sqrtf(p.bn3[3 * D + k] + 1e-5f);
+    float d = (x[k] > 0.f) ? dx * a3 : 0.f;
+    if (p.p_hid > 0.f) d *= kp_drop_scale(p.seed, pair, p.step, KP_DROP_HIDDEN + k, p.p_hid);
+    p.dh[(size_t)g * D + k] = d;
+  }
+  if (tid == 0) p.colcoef[g] = (sM - (p.ta * (m_pos ? 1.f : 0.f) + p.tb)) * scale;
+}
+
+// One WARP per pair (D = 200: seven elements per lane, no block-wide barriers): from a few thousand pairs on.
 __global__ void __launch_bounds__(CT) cv_dx(const CvDx p) {
   const int g = blockIdx.x * (CT / 32) + (threadIdx.x >> 5), lane = threadIdx.x & 31, D = p.D;
   if (g >= p.GA) return;
@@ -374,7 +409,8 @@ int kp_conve_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cuda
       d.a_cand = pl.a_cand; d.a_pair = pl.a_truth; d.nA = pl.nA; d.nB = pl.nB;
       d.pos_off = b->pos_off; d.pos_ids = b->pos_ids; d.xA = xA; d.pO = pO; d.mim = mim; d.dh = dh; d.colcoef = colcoef;
       d.seed = seed; d.step = (int)t; d.p_hid = ctx->cv.drop_hid;
-      cv_dx<<<(int)((GA + CT / 32 - 1) / (CT / 32)), CT, 0, st>>>(d);
+      if (GA < 4096) cv_dx_block<<<(int)GA, CT, (size_t)D * 4, st>>>(d);
+      else cv_dx<<<(int)((GA + CT / 32 - 1) / (CT / 32)), CT, 0, st>>>(d);
       CvBack k;
       k.GA = (int)GA; k.D = D; k.H = ctx->cv.H; k.F = ctx->cv.n_filters; k.hidden = hidden;
       k.conv_w = ctx->cv.conv_w; k.bn1 = ctx->cv.bn1; k.bn2 = ctx->cv.bn2;

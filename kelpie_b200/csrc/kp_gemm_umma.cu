@@ -30,6 +30,7 @@ static_assert(G_SMEM <= 232448, "shared memory budget of one CTA");
 
 struct GK_ {
   int M, N, KB, ksteps, n_tiles, tiles_per_strip, kb_per_split;  // kb_per_split > 0: split-K over blockIdx.z, C accumulated with reductions
+  long long part_stride;  // > 0 (with kb_per_split): split z stores its partial sums at C + z * part_stride instead (summed in a fixed order by the caller)
   int nt;  // columns of C per accumulator tile: 128, or up to 256 (a multiple of 16): A is then streamed once per 256 columns and an
            // MMA reads 4 KB of A + nt / 64 KB of B per nt / 2 cycles -- 64 B/clk at nt = 256 instead of 96, under the shared-memory port
   float* C;
@@ -207,7 +208,9 @@ gemm_umma_kernel(const __grid_constant__ CUtensorMap bh64_map, const __grid_cons
           if (m0 + R < p.M && col < p.N) {
 
             float* dst = p.C + (m0 + R) * p.ldc + col;
-            if (p.kb_per_split > 0)
+            if (p.part_stride > 0)
+              *reinterpret_cast<float4*>(dst + (long long)blockIdx.z * p.part_stride) = v;
+            else if (p.kb_per_split > 0)
               asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
             else
               *reinterpret_cast<float4*>(dst) = v;
@@ -378,6 +381,7 @@ int kp_gemm_umma_dyn(kp_ctx* ctx, const float* A, long long lda, bool transA, in
     ksplit = (p.KB + p.kb_per_split - 1) / p.kb_per_split;
     KP_CUDA(ctx, cudaMemset2DAsync(C, (size_t)ldc * 4, 0, (size_t)Nc * 4, (size_t)M, st));
   }
+  p.part_stride = 0;
   p.C = C;
   p.ldc = ldc;
   KP_SMEM_ONCE(ctx, (gemm_umma_kernel<false>), G_SMEM);
@@ -445,7 +449,21 @@ int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umm
 
 // The same with A already split by its producer: bf16 hi / lo [M rounded up to 256, B.Kpad], columns K..Kpad zero (rows beyond M
 // are read but their results are not stored).
-int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const kp_umma_b& B, float* C, long long ldc, cudaStream_t st) {
+// Few rows and a long K (the forward Linear layer of an explain-sized batch: one pair of CTAs, 152 k-blocks): K is cut over up to half
+// the SMs' worth of CTA pairs; every part stores its own partial result and the caller adds them in a fixed order (no atomics: the
+// sum does not depend on the schedule).
+int kp_gemm_umma_ksplit(const kp_ctx* ctx, int M, const kp_umma_b& B) {
+  const int clusters = (M + 255) / 256, KB = B.Kpad / 64;
+  if (!ctx->gemm_ksplit || B.N > 256 || KB < 16) return 1;
+  int ks = (ctx->sm_count / 2) / clusters;
+  if (ks > KB / 4) ks = KB / 4;
+  if (ks < 2) return 1;
+  const int per = (KB + ks - 1) / ks;
+  return (KB + per - 1) / per;
+}
+
+int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const kp_umma_b& B, float* C, long long ldc, cudaStream_t st,
+                       float* parts) {
   if (M <= 0) return KP_OK;
   if (B.N % 4 != 0 || ldc % 4 != 0) KP_FAIL(ctx, KP_EINVAL, "tcgen05 GEMM needs N and ldc multiple of 4");
   const int n_mt = ((M + 255) / 256) * 2;
@@ -469,10 +487,18 @@ int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const
   const int n_strips = (p.n_tiles + p.tiles_per_strip - 1) / p.tiles_per_strip;
   p.C = C;
   p.ldc = ldc;
+  p.part_stride = 0;
+  const int ks = parts ? kp_gemm_umma_ksplit(ctx, M, B) : 1;  // parts: room for kp_gemm_umma_ksplit() x [M, ldc]; then C is NOT written
+  if (ks > 1) {
+    if (n_strips != 1) KP_FAIL(ctx, KP_EINVAL, "split-K GEMM expects one accumulator tile per row block");
+    p.kb_per_split = (p.KB + ks - 1) / ks;
+    p.part_stride = (long long)M * ldc;
+    p.C = parts;
+  }
   KP_SMEM_ONCE(ctx, (gemm_umma_kernel<false>), G_SMEM);
   {
     KpTimer timer(ctx, kp_ctx::T_CONV, st);
-    gemm_umma_kernel<false><<<dim3(n_mt, n_strips, 1), GT, G_SMEM, st>>>(B.hi64, B.lo64, ah_map, al_map, p);
+    gemm_umma_kernel<false><<<dim3(n_mt, n_strips, ks), GT, G_SMEM, st>>>(B.hi64, B.lo64, ah_map, al_map, p);
   }
   KP_LAUNCHED(ctx, 1);
   return KP_OK;

@@ -89,6 +89,9 @@ struct kp_ctx {
                                // 256 tiles = 2048 K-steps bound it at 1.2e-4 of O; the strips are merged in fp32 (round to nearest).
   int64_t umma_qres = 1;  // pair kernel (rows of <= 256 floats): query tile resident in shared memory (kp_flash_umma2.cu)
   int64_t conv_split = 1;  // ConvE conv kernel emits the Linear GEMM's bf16 hi / lo operand directly (kp_conve.cu)
+  int64_t gemm_ksplit = 1;   // forward Linear layer of few rows: K cut over CTA pairs, partial sums added in a fixed order (kp_gemm_umma.cu)
+  int64_t umma_fc_min_rows = 128;  // ConvE Linear layer on tcgen05 from this many pairs on; below, the fp32 FMA chains of kp_gemm.cu (explain-sized
+                                   // batches: 3 % slower than tcgen05 from 16 pairs on, but ranks among saturated sigmoid scores follow the reference more closely)
   int64_t gemm_wide = 1;  // ConvE Linear layer GEMMs with accumulator tiles of up to 256 columns (kp_gemm_umma.cu)
   int64_t umma_fc = 1;      // ConvE Linear layer on the tensor cores (kp_gemm_umma.cu) from 128 rows on
   int64_t umma_rank = 1;    // filtered rank of >= 128 DOT queries on the tensor cores with an exact fp32 re-check (kp_rank_umma.cu)
@@ -261,7 +264,11 @@ int kp_umma_b_prepare(kp_ctx* ctx, const float* B, int N, int K, bool transpose,
 int kp_gemm_umma(kp_ctx* ctx, const float* A, long long lda, int M, const kp_umma_b& B, float* C, long long ldc, size_t ws_offset,
                  cudaStream_t st);
 size_t kp_gemm_umma_a_bytes(int M, const kp_umma_b& B);
-int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const kp_umma_b& B, float* C, long long ldc, cudaStream_t st);
+// parts (optional): room for kp_gemm_umma_ksplit(ctx, M, B) x [M, ldc] partial results; when that count is > 1, K is cut over that many
+// CTA pairs per tile, C is NOT written and the caller sums parts[z * M * ldc + ...] over z in order
+int kp_gemm_umma_ksplit(const kp_ctx* ctx, int M, const kp_umma_b& B);
+int kp_gemm_umma_split(kp_ctx* ctx, const void* ah, const void* al, int M, const kp_umma_b& B, float* C, long long ldc, cudaStream_t st,
+                       float* parts = nullptr);
 // ConvE Linear layer: forward (x = feat W^T) / backward (dfeat = dh W); tcgen05 from 128 rows on, else CUDA cores
 int kp_conve_fc(kp_ctx* ctx, bool forward, int M, const float* A, float* C, size_t ws_offset, cudaStream_t st);
 // Whether the forward Linear layer of M pairs runs on tcgen05: the conv kernel then writes the feature maps as the GEMM's split

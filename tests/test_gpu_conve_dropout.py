@@ -129,7 +129,10 @@ def test_conv_kernel_split_output_is_the_split_pass(rates):
         b.add(facts, rng.random(D).astype(np.float32))
     arrs = b.arrays()
     rows = {}
-    for name, opts in (("split", {}), ("fp32", {"conv_split": 0}), ("simt", {"umma_fc": 0})):
+    # gemm_ksplit (default on) cuts the forward Linear layer's K over several CTA pairs when there are few rows and adds the partial
+    # results in a fixed order: other roundings than one accumulation chain, but the same bits every run
+    for name, opts in (("split", {"gemm_ksplit": 0}), ("fp32", {"conv_split": 0, "gemm_ksplit": 0}), ("simt", {"umma_fc": 0}),
+                       ("ksplit", {}), ("ksplit_again", {})):
         ctx = runtime.Context("ConvE", z["w_ent"], z["w_rel"], conve=conve)
         for k, v in opts.items():
             ctx.set_option(k, v)
@@ -137,3 +140,5 @@ def test_conv_kernel_split_output_is_the_split_pass(rates):
     assert np.isfinite(rows["split"]).all()
     assert np.array_equal(rows["split"], rows["fp32"])
     assert np.abs(rows["split"] - rows["simt"]).max() <= 1e-4 * np.abs(rows["simt"]).max()
+    assert np.array_equal(rows["ksplit"], rows["ksplit_again"])
+    assert np.abs(rows["ksplit"] - rows["simt"]).max() <= 1e-4 * np.abs(rows["simt"]).max()
