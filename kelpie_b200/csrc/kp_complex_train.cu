@@ -50,26 +50,41 @@ __global__ void cx_lse(int G, int n_strips, const float* __restrict__ pm, const 
 // Strips of row g folded into strip 0 in place (same order and weights as a sequential merge): one CTA per row, so the
 // per-candidate update below walks one strip per row instead of n_strips (it runs one CTA per candidate; with a
 // handful of candidates per batch -- the explain path -- the serial merge was 57 % of the device time).
-constexpr int MRG_THREADS = 128;
-__global__ void __launch_bounds__(MRG_THREADS) cx_merge_strips(int GA, int D, int n_strips, float* __restrict__ pm,
-                                                              float* __restrict__ pl, float* __restrict__ pO) {
-  extern __shared__ float wgt[];  // [n_strips] e^{m_s - M}, < 0 = empty strip
-  const int g = blockIdx.x, tid = threadIdx.x;
+// One CTA per row, one thread per output dim (up to 1024 threads; the strips' maxima / sums are loaded by all threads in parallel and
+// folded in strip order from shared memory, the partial rows 16 loads in flight per thread): with the 64 strips of an explain-sized
+// batch the kernel is a few dependent round trips to the L2 long instead of ~100.
+constexpr int MRG_MAX_THREADS = 1024;
+__global__ void __launch_bounds__(MRG_MAX_THREADS) cx_merge_strips(int GA, int D, int n_strips, float* __restrict__ pm,
+                                                                  float* __restrict__ pl, float* __restrict__ pO) {
+  extern __shared__ float wgt[];  // [n_strips] e^{m_s - M}, < 0 = empty strip | [n_strips] l_s
+  __shared__ float red[MRG_MAX_THREADS / 32];
+  float* ls = wgt + n_strips;
+  const int g = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
   float M = -INFINITY;
-  for (int s = 0; s < n_strips; ++s) M = fmaxf(M, pm[(size_t)s * GA + g]);
-  for (int s = tid; s < n_strips; s += MRG_THREADS) {
+  for (int s = tid; s < n_strips; s += nt) {
     const float ms = pm[(size_t)s * GA + g];
+    wgt[s] = ms;
+    ls[s] = pl[(size_t)s * GA + g];
+    M = fmaxf(M, ms);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  if ((tid & 31) == 0) red[tid >> 5] = M;
+  __syncthreads();
+  for (int w = 0; w < (nt + 31) / 32; ++w) M = fmaxf(M, red[w]);
+  for (int s = tid; s < n_strips; s += nt) {
+    const float ms = wgt[s];
     wgt[s] = (ms != -INFINITY) ? expf(ms - M) : -1.f;
   }
   __syncthreads();
-  for (int k = tid; k < D; k += MRG_THREADS) {
+  for (int k = tid; k < D; k += nt) {
     float ok = 0.f;
-    for (int s0 = 0; s0 < n_strips; s0 += 8) {  // 8 partials in flight per thread, folded in strip order
-      float v[8];
+    for (int s0 = 0; s0 < n_strips; s0 += 16) {  // 16 partials in flight per thread, folded in strip order
+      float v[16];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) v[j] = (s0 + j < n_strips) ? pO[((size_t)(s0 + j) * GA + g) * D + k] : 0.f;
+      for (int j = 0; j < 16; ++j) v[j] = (s0 + j < n_strips) ? pO[((size_t)(s0 + j) * GA + g) * D + k] : 0.f;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
+      for (int j = 0; j < 16; ++j) {
         const float w = (s0 + j < n_strips) ? wgt[s0 + j] : -1.f;
         if (w >= 0.f) ok += v[j] * w;
       }
@@ -80,7 +95,7 @@ __global__ void __launch_bounds__(MRG_THREADS) cx_merge_strips(int GA, int D, in
     float L = 0.f;
     for (int s = 0; s < n_strips; ++s) {
       const float w = wgt[s];
-      if (w >= 0.f) L += pl[(size_t)s * GA + g] * w;
+      if (w >= 0.f) L += ls[s] * w;
     }
     pm[g] = M;
     pl[g] = L;
@@ -322,7 +337,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       if ((rc = kp_flash_run(ctx, qA, (int)GA, KP_FLASH_SOFTMAX, pm, plv, pO, st, &ns)) != KP_OK) return rc;
     }
     if (GA > 0 && ns > 1 && ctx->cx_merge) {
-      cx_merge_strips<<<(int)GA, MRG_THREADS, (size_t)ns * sizeof(float), st>>>((int)GA, D, ns, pm, plv, pO);
+      cx_merge_strips<<<(int)GA, D >= MRG_MAX_THREADS ? MRG_MAX_THREADS : ((D + 31) / 32) * 32, (size_t)2 * ns * sizeof(float), st>>>((int)GA, D, ns, pm, plv, pO);
       KP_LAUNCHED(ctx, 1);
       ns = 1;
     }
