@@ -39,6 +39,10 @@ extern "C" int kp_set_option(kp_ctx* ctx, const char* name, int64_t value) {
     ctx->skinny_fc = value;
     return KP_OK;
   }
+  if (!strcmp(name, "cx_rowgrad")) {
+    ctx->cx_rowgrad = value;
+    return KP_OK;
+  }
   if (!strcmp(name, "cx_merge")) {
     ctx->cx_merge = value;
     return KP_OK;

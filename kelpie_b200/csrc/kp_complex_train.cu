@@ -122,6 +122,10 @@ struct CxUpd {
   float* mim;           // [C, D]
   float* st1;           // [C, D] Adagrad sum / Adam exp_avg
   float* st2;           // [C, D] Adam exp_avg_sq
+  // staged != 0: cx_row_grad ran first -- pO[g, :] holds row g's gradient contribution and coefB[b] the coefficient of B row b
+  int staged;
+  const float* coefB;   // [GB]
+  const int32_t *a_cand, *b_cand;
 };
 
 constexpr int UPD_THREADS = 256;
@@ -136,6 +140,99 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
 #pragma unroll
   for (int w = 0; w < UPD_THREADS / 32; ++w) s += red[w];
   return s;
+}
+
+// Per-ROW stage of the update (one CTA per row of the step, A rows then B rows), so that the per-candidate kernel below is left with
+// plain sums: for an A row the strips are merged (as cx_merge_strips does), then the row's softmax statistics, dq and its
+// contribution to the mimic row's gradient are computed with the expressions -- and the 256-thread reduction order -- of the
+// per-candidate loop it replaces, and the contribution overwrites pO[g, :]; for a B row only the coefficient is needed.
+// With the 5-10 rows per candidate of an explain-sized batch this takes the row loop (a block reduction and two barriers per
+// row) off the critical path of 6 CTAs and spreads it over ~100.
+__global__ void __launch_bounds__(UPD_THREADS) cx_row_grad(const CxUpd p, int GB, float* __restrict__ pm, float* __restrict__ pl,
+                                                          float* __restrict__ pO, float* __restrict__ coefB) {
+  extern __shared__ float usm[];
+  const int D = p.D, d = D >> 1, tid = threadIdx.x;
+  float* eM = usm;        // [D]
+  float* dq = eM + D;     // [D]
+  float* qv = dq + D;     // [D]
+  float* wgt = qv + D;    // [n_strips]
+  float* ls = wgt + p.n_strips;
+  __shared__ float red[UPD_THREADS / 32];
+  if ((int)blockIdx.x >= p.GA) {
+    const int b = blockIdx.x - p.GA;
+    if (b >= GB) return;
+    const int c = p.b_cand[b];
+    const float invB = 1.f / (float)(p.nA[c] + p.nB[c]);
+    float part = 0.f;
+    for (int k = tid; k < D; k += UPD_THREADS) part = __fmaf_rn(p.qB[(size_t)b * D + k], p.mim[(size_t)c * D + k], part);
+    const float z = block_sum(part, red);
+    const float lse = p.lseB[b];
+    const float mx = fmaxf(lse, z);
+    const float eS = expf(z - mx);
+    const float pM = eS / (expf(lse - mx) + eS);
+    if (tid == 0) coefB[b] = (pM - 1.f) * invB;  // the truth of a B row is the mimic itself
+    return;
+  }
+  const int g = blockIdx.x, c = p.a_cand[g], GA = p.GA, ns = p.n_strips;
+  const float invB = 1.f / (float)(p.nA[c] + p.nB[c]);
+  float M = -INFINITY;
+  for (int s = tid; s < ns; s += UPD_THREADS) {
+    const float ms = pm[(size_t)s * GA + g];
+    wgt[s] = ms;
+    ls[s] = pl[(size_t)s * GA + g];
+    M = fmaxf(M, ms);
+  }
+  float part = 0.f;
+  for (int k = tid; k < D; k += UPD_THREADS) {
+    const float qk = p.qA[(size_t)g * D + k], ek = p.mim[(size_t)c * D + k];
+    eM[k] = ek;
+    qv[k] = qk;
+    part = __fmaf_rn(qk, ek, part);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) M = fmaxf(M, __shfl_xor_sync(0xffffffffu, M, o));
+  if ((tid & 31) == 0) red[tid >> 5] = M;
+  __syncthreads();
+#pragma unroll
+  for (int w = 0; w < UPD_THREADS / 32; ++w) M = fmaxf(M, red[w]);
+  for (int s = tid; s < ns; s += UPD_THREADS) {
+    const float ms = wgt[s];
+    wgt[s] = (ms != -INFINITY) ? expf(ms - M) : -1.f;
+  }
+  const float zM = block_sum(part, red);  // (its barriers also publish wgt / ls / eM)
+  float L = 0.f;
+  for (int s = 0; s < ns; ++s) {
+    const float w = wgt[s];
+    if (w >= 0.f) L += ls[s] * w;
+  }
+  const float mx = fmaxf(M, zM);
+  const float eF = L * expf(M - mx), eS = expf(zM - mx);
+  const float den = eF + eS;
+  const float pM = eS / den;
+  const int o = p.a_truth[g];
+  const float* Eo = (o == p.N) ? eM : p.ent + (size_t)o * D;
+  for (int k = tid; k < D; k += UPD_THREADS) {
+    float ok = 0.f;
+    for (int s0 = 0; s0 < ns; s0 += 16) {  // 16 partials in flight per thread, folded in strip order
+      float v[16];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) v[j] = (s0 + j < ns) ? pO[((size_t)(s0 + j) * GA + g) * D + k] : 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const float w = (s0 + j < ns) ? wgt[s0 + j] : -1.f;
+        if (w >= 0.f) ok += v[j] * w;
+      }
+    }
+    dq[k] = (ok * (expf(M - mx) / den) + pM * eM[k] - Eo[k]) * invB;
+  }
+  __syncthreads();
+  const float* rho = p.rel + (size_t)p.a_rel[g] * D;
+  const float colM = (pM - (o == p.N ? 1.f : 0.f)) * invB;
+  for (int k = tid; k < d; k += UPD_THREADS) {
+    const float rr = rho[k], ri = rho[d + k], da = dq[k], db = dq[d + k];
+    pO[(size_t)g * D + k] = da * rr + db * ri + colM * qv[k];
+    pO[(size_t)g * D + d + k] = -da * ri + db * rr + colM * qv[d + k];
+  }
 }
 
 __global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
@@ -157,7 +254,15 @@ __global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
   }
   __syncthreads();
 
-  for (int64_t g = p.aoff[c]; g < p.aoff[c] + nA; ++g) {
+  if (p.staged) {  // rows already reduced to their contributions: sum them in row order (a thread owns its dims: no barriers)
+    for (int k = tid; k < D; k += UPD_THREADS) {
+      float acc = 0.f;
+      for (int64_t g = p.aoff[c]; g < p.aoff[c] + nA; ++g) acc += p.pO[(size_t)g * D + k];
+      for (int64_t b = p.boff[c]; b < p.boff[c] + nB; ++b) acc += p.coefB[b] * p.qB[(size_t)b * D + k];
+      grad[k] = acc;
+    }
+  }
+  for (int64_t g = p.aoff[c]; !p.staged && g < p.aoff[c] + nA; ++g) {
     float M, L;
     kp_flash_merge_stats(p.pm, p.pl, p.n_strips, p.GA, (int)g, M, L);
     float part = 0.f;
@@ -191,7 +296,7 @@ __global__ void __launch_bounds__(UPD_THREADS) cx_update(const CxUpd p) {
     }
     __syncthreads();
   }
-  for (int64_t b = p.boff[c]; b < p.boff[c] + nB; ++b) {
+  for (int64_t b = p.boff[c]; !p.staged && b < p.boff[c] + nB; ++b) {
     float part = 0.f;
     for (int k = tid; k < D; k += UPD_THREADS) {
       const float qk = p.qB[(size_t)b * D + k];
@@ -274,7 +379,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
   need += 3 * WsCursor::need(C, 4) + 2 * WsCursor::need(C + 1, 8);
   need += 6 * WsCursor::need(G, 4);
   need += 2 * WsCursor::need((size_t)Gpad * D, 4);      // qA, qB
-  need += WsCursor::need(G, 4);                          // lseB
+  need += 2 * WsCursor::need(G, 4);                      // lseB, coefB
   need += 2 * WsCursor::need(SG, 4) + WsCursor::need(SG * D, 4);
   int rc = kp_ws_reserve(ctx, need);
   if (rc != KP_OK) return rc;
@@ -292,6 +397,7 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
   float* qA = ws.take<float>((size_t)Gpad * D);
   float* qB = ws.take<float>((size_t)Gpad * D);
   float* lseB = ws.take<float>(G);
+  float* coefB = ws.take<float>(G);
   float* pm = ws.take<float>(SG);
   float* plv = ws.take<float>(SG);
   float* pO = ws.take<float>(SG * D);
@@ -336,7 +442,8 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       KP_LAUNCHED(ctx, 1);
       if ((rc = kp_flash_run(ctx, qA, (int)GA, KP_FLASH_SOFTMAX, pm, plv, pO, st, &ns)) != KP_OK) return rc;
     }
-    if (GA > 0 && ns > 1 && ctx->cx_merge) {
+    const bool staged = ctx->cx_rowgrad != 0 && ctx->cx_merge != 0;
+    if (GA > 0 && ns > 1 && ctx->cx_merge && !staged) {
       cx_merge_strips<<<(int)GA, D >= MRG_MAX_THREADS ? MRG_MAX_THREADS : ((D + 31) / 32) * 32, (size_t)2 * ns * sizeof(float), st>>>((int)GA, D, ns, pm, plv, pO);
       KP_LAUNCHED(ctx, 1);
       ns = 1;
@@ -353,6 +460,11 @@ int kp_complex_post_train(kp_ctx* ctx, const kp_pt_batch* b, const kp_hp* hp, cu
       u.a_rel = pl.a_rel; u.a_truth = pl.a_truth;
       u.qA = qA; u.pm = pm; u.pl = plv; u.pO = pO; u.qB = qB; u.lseB = lseB;
       u.mim = mim; u.st1 = st1; u.st2 = st2;
+      u.staged = staged ? 1 : 0; u.coefB = coefB; u.a_cand = pl.a_cand; u.b_cand = pl.b_cand;
+      if (staged) {
+        cx_row_grad<<<(int)(GA + GB), UPD_THREADS, ((size_t)3 * D + 2 * ns) * sizeof(float), st>>>(u, (int)GB, pm, plv, pO, coefB);
+        KP_LAUNCHED(ctx, 1);
+      }
       cx_update<<<C, UPD_THREADS, (size_t)4 * D * sizeof(float), st>>>(u);
       KP_LAUNCHED(ctx, 1);
     }

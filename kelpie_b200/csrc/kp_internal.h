@@ -74,6 +74,7 @@ struct kp_ctx {
   unsigned long long* rank_recheck_total = nullptr;  // device counter: pairs the tensor-core rank pass handed to the exact re-check
   int64_t force_simt = 0;
   int64_t skinny_fc = 1;      // ConvE Linear forward of < 128 rows on the skinny kernel (else the tiled CUDA-core GEMM)
+  int64_t cx_rowgrad = 1;     // ComplEx: per-row stage (strip merge + row gradient, one CTA per row) ahead of the per-candidate update
   int64_t cx_merge = 1;       // ComplEx: strips merged per row by cx_merge_strips before the per-candidate update
   int64_t umma_min_rows = 1;  // fused pass on tcgen05 from this many rows on (one 128-row tile costs the same for 1..128 rows:
                               // 43 us vs 164 us for the CUDA-core pass at 24 620 x 400); 32 = the earlier threshold
