@@ -303,6 +303,11 @@ int kp_mt19937_words(uint32_t* key, int32_t* pos, int64_t count, uint32_t* out);
 int kp_replay_transe_corruptions(uint32_t* key, int32_t* pos, int32_t epochs, int64_t drawn, int64_t used, uint32_t high,
                                  int32_t* neg_code);
 int kp_replay_numpy_shuffles(uint32_t* key, int32_t* pos, int32_t epochs, int32_t n, int32_t* perm);
+/* Both of the above for one TransE job in one call (pairwise_ranking_optimizer.py:165-195): torch's generator travels as the
+ * 5056-byte buffer of torch.get_rng_state() and is updated in place; pos_idx[e * n + i] = index of the positive of training
+ * row i of epoch e (= shuffled row i / ratio), neg_code as kp_replay_transe_corruptions with drawn = ratio * n, used = n. */
+int kp_replay_transe_job(uint32_t* np_key, int32_t* np_pos, uint8_t* torch_state, int64_t torch_state_bytes, int32_t epochs,
+                         int32_t n, int32_t ratio, uint32_t high, int32_t* pos_idx, int32_t* neg_code);
 
 /* Diagnostic: the fused score -> softmax (mode 0) / sigmoid (mode 1) -> contract pass alone, for
  * n_rows query vectors [n_rows, D] (device) against the resident entity table:

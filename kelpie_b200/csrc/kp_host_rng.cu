@@ -13,6 +13,8 @@
 // exactly as the reference's calls would.  The mirror checks these against torch / numpy themselves once
 // per process and keeps the per-call path where they do not reproduce (another generator layout).
 #include <cstdint>
+#include <cstring>
+#include <vector>
 
 #include "../../include/kelpie_b200.h"
 
@@ -113,6 +115,65 @@ int kp_replay_numpy_shuffles(uint32_t* key, int32_t* pos, int32_t epochs, int32_
     }
   }
   *pos = t.pos;
+  return KP_OK;
+}
+
+// One TransE post-training job in one call: the shuffles (numpy's generator) and the corruptions (torch's generator, handed in
+// as the 5056-byte buffer of torch.get_rng_state(): seed u64 | left i32 | seeded i32 | next u64 | 624 key words as u64 | normal
+// cache) of kp_replay_numpy_shuffles + kp_replay_transe_corruptions, with the positive of training row i of an epoch =
+// shuffled row i / ratio (the first n rows of np.repeat(rows, ratio)).  Both generators end as after the separate calls.
+int kp_replay_transe_job(uint32_t* np_key, int32_t* np_pos, uint8_t* torch_state, int64_t torch_state_bytes, int32_t epochs, int32_t n,
+                         int32_t ratio, uint32_t high, int32_t* pos_idx, int32_t* neg_code) {
+  constexpr int64_t T_BYTES = 5056;
+  if (bad_state(np_key, np_pos) || !torch_state || torch_state_bytes != T_BYTES || epochs < 0 || n < 0 || ratio < 1 || high == 0 ||
+      high > 0x80000000u || ((!pos_idx || !neg_code) && (int64_t)epochs * n > 0))
+    return KP_EINVAL;
+  int32_t left;
+  uint64_t next;
+  memcpy(&left, torch_state + 8, 4);
+  memcpy(&next, torch_state + 16, 8);
+  uint32_t tkey[MT_N];
+  for (int i = 0; i < MT_N; ++i) {
+    uint64_t w;
+    memcpy(&w, torch_state + 24 + 8 * i, 8);
+    tkey[i] = (uint32_t)w;
+  }
+  int32_t tpos = (left == 1 && next == 0) ? MT_N : (int32_t)next;  // freshly seeded: regenerate first
+  if (tpos < 0 || tpos > MT_N) return KP_EINVAL;
+  Twister nt{np_key, *np_pos}, tt{tkey, tpos};
+  std::vector<int32_t> perm((size_t)n);
+  for (int32_t i = 0; i < n; ++i) perm[i] = i;
+  const int64_t drawn = (int64_t)ratio * n;
+  for (int32_t e = 0; e < epochs; ++e) {
+    for (int32_t i = n - 1; i >= 1; --i) {  // np.random.shuffle: the reference keeps shuffling the same array
+      uint32_t mask = (uint32_t)i;
+      mask |= mask >> 1, mask |= mask >> 2, mask |= mask >> 4, mask |= mask >> 8, mask |= mask >> 16;
+      uint32_t j;
+      while ((j = nt.next() & mask) > (uint32_t)i) {
+      }
+      const int32_t tmp = perm[i];
+      perm[i] = perm[j];
+      perm[j] = tmp;
+    }
+    int32_t* prow = pos_idx + (int64_t)e * n;
+    int32_t* crow = neg_code + (int64_t)e * n;
+    for (int32_t i = 0; i < n; ++i) prow[i] = perm[i / ratio];
+    for (int32_t i = 0; i < n; ++i) crow[i] = (int32_t)(tt.next() % high);  // torch.randint(high, (ratio * n,))[:n]
+    tt.skip(drawn - n);
+    for (int32_t i = 0; i < n; ++i) crow[i] = (int32_t)((uint32_t)crow[i] | ((tt.next() & 1u) << 31));  // randint(2, ...)
+    tt.skip(drawn - n);
+  }
+  *np_pos = nt.pos;
+  for (int i = 0; i < MT_N; ++i) {
+    const uint64_t w = tkey[i];
+    memcpy(torch_state + 24 + 8 * i, &w, 8);
+  }
+  next = (uint64_t)tt.pos;
+  left = MT_N + 1 - tt.pos;  // torch keeps left + next == 625
+  const int32_t seeded = 1;
+  memcpy(torch_state + 16, &next, 8);
+  memcpy(torch_state + 8, &left, 4);
+  memcpy(torch_state + 12, &seeded, 4);
   return KP_OK;
 }
 

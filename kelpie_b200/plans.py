@@ -88,6 +88,21 @@ class HostReplay:
         cls.torch_commit(buf, key, pos)
         return code
 
+    @classmethod
+    def transe_job(cls, E, n, ratio, high):
+        """numpy_shuffles + transe_corruptions of one job in ONE native call (kp_replay_transe_job), torch's generator state
+        handed over as the get_rng_state() buffer itself: (pos_idx [E * n] int32, neg_code [E * n] int32)."""
+        pos_idx = np.empty(E * n, dtype=np.int32)
+        code = np.empty(E * n, dtype=np.int32)
+        state = torch.get_rng_state()
+        addr = cls._numpy_addr()
+        rc = cls.lib().kp_replay_transe_job(addr, addr + 4 * cls._N, state.data_ptr(), state.numel(), E, n, ratio, high,
+                                            pos_idx.ctypes.data, code.ctypes.data)
+        if rc != 0:
+            raise RuntimeError(f"kp_replay_transe_job failed ({rc}): unknown torch CPU generator state layout?")
+        torch.set_rng_state(state)
+        return pos_idx, code
+
     # ---- numpy's legacy global RandomState
     @classmethod
     def _numpy_addr(cls):
@@ -160,6 +175,22 @@ class HostReplay:
                         np.random.shuffle(idx)
                         ok = ok and np.array_equal(perm[e], idx)
                     ok = ok and np.array_equal(tail_n, np.random.random(3))
+                    # the fused per-job call against torch / numpy themselves, and where it leaves both generators
+                    torch.set_rng_state(start_t)
+                    np.random.set_state(start_n)
+                    pi, cd = cls.transe_job(2, 11, 5, 24621)
+                    end_t, end_n = torch.rand(3), np.random.random(2)
+                    torch.set_rng_state(start_t)
+                    np.random.set_state(start_n)
+                    idx = np.arange(11)
+                    for e in range(2):
+                        np.random.shuffle(idx)
+                        rnd = torch.randint(24621, (55,)).numpy()[:11]
+                        coin = torch.randint(2, (55,)).numpy()[:11]
+                        ref = (rnd | (coin << 31)).astype(np.uint32).view(np.int32)
+                        ok = ok and np.array_equal(pi[e * 11:(e + 1) * 11], idx[np.arange(11) // 5])
+                        ok = ok and np.array_equal(cd[e * 11:(e + 1) * 11], ref)
+                    ok = ok and torch.equal(end_t, torch.rand(3)) and np.array_equal(end_n, np.random.random(2))
                 cls._ok = bool(ok)
             except Exception:
                 cls._ok = False
@@ -202,8 +233,11 @@ def draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng=Non
         rnd = fast_rng.integers(0, n_ent_with_mimic, (E, n))
         coin = fast_rng.integers(0, 2, (E, n))
     elif n_ent_with_mimic < HostReplay.MAX_HIGH and HostReplay.available():
-        # numpy's generator is independent of torch's: all shuffles first, same numbers
-        perm = HostReplay.numpy_shuffles(E, n)
+        # numpy's generator is independent of torch's: interleaving the shuffles with the corruptions draws the same numbers
+        if os.environ.get("KELPIE_HOST_REPLAY") != "split":
+            pos_idx, code = HostReplay.transe_job(E, n, ratio, n_ent_with_mimic)
+            return n, rows.astype(np.int32), pos_idx, code
+        perm = HostReplay.numpy_shuffles(E, n)  # A/B: the two separate native calls
         code = HostReplay.transe_corruptions(E, ratio * n, n, n_ent_with_mimic)
         return n, rows.astype(np.int32), perm[:, take].reshape(-1), code
     else:

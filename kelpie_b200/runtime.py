@@ -23,7 +23,7 @@ EXPORTS = [
     "kp_filter_build", "kp_filter_download",
     "kp_all_scores", "kp_score_triples", "kp_filtered_rank", "kp_post_train_batch", "kp_launch_count", "kp_set_option", "kp_stat",
     "kp_debug_contract", "kp_dp_relevance",
-    "kp_mt19937_words", "kp_replay_transe_corruptions", "kp_replay_numpy_shuffles",
+    "kp_mt19937_words", "kp_replay_transe_corruptions", "kp_replay_numpy_shuffles", "kp_replay_transe_job",
     "kp_transe_fit_create", "kp_transe_fit_steps", "kp_transe_fit_destroy", "kp_transe_fit_error", "kp_transe_fit_launches",
     "kp_complex_fit_create", "kp_complex_fit_steps", "kp_complex_fit_destroy", "kp_complex_fit_error", "kp_complex_fit_launches",
     "kp_conve_fit_create", "kp_conve_fit_steps", "kp_conve_fit_destroy", "kp_conve_fit_error", "kp_conve_fit_launches",
@@ -113,6 +113,8 @@ def load_library():
     lib.kp_replay_transe_corruptions.restype = c_int
     lib.kp_replay_numpy_shuffles.argtypes = [c_void_p, c_void_p, c_int32, c_int32, c_void_p]
     lib.kp_replay_numpy_shuffles.restype = c_int
+    lib.kp_replay_transe_job.argtypes = [c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, ctypes.c_uint32, c_void_p, c_void_p]
+    lib.kp_replay_transe_job.restype = c_int
     lib.kp_transe_fit_create.argtypes = [c_int, c_int64, c_int64, c_int32, c_int32, ctypes.c_float, ctypes.c_float,
                                          ctypes.c_float, c_void_p, c_void_p, POINTER(c_void_p)]
     lib.kp_transe_fit_create.restype = c_int

@@ -324,8 +324,14 @@ def test_native_replay_and_per_call_draws_agree():
         finally:
             plans.HostReplay._ok = saved
 
-    a, b = run(True), run(False)
+    a, b = run(True), run(False)  # native: one fused call per TransE job (kp_replay_transe_job)
     assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
+    os.environ["KELPIE_HOST_REPLAY"] = "split"  # the two separate native calls (shuffles, corruptions)
+    try:
+        c = run(True)
+    finally:
+        del os.environ["KELPIE_HOST_REPLAY"]
+    assert len(a) == len(c) and all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, c))
 
 
 def test_mt19937_words_match_numpy_bit_generator():
