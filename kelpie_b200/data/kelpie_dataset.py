@@ -41,7 +41,7 @@ class KelpieDataset:
         self.kelpie_training_triples = rep(dataset.entity_to_training_triples[entity], entity, self.kelpie_entity)
         self.kelpie_validation_triples = rep(dataset.entity_to_validation_triples[entity], entity, self.kelpie_entity)
         self.kelpie_testing_triples = rep(dataset.entity_to_testing_triples[entity], entity, self.kelpie_entity)
-        self.kelpie_training_triples_copy = copy.deepcopy(self.kelpie_training_triples)
+        self.kelpie_training_triples_copy = list(self.kelpie_training_triples)  # rows are immutable tuples: as good as the reference's deepcopy
         R = self.num_relations
         for s, p, o in self.kelpie_training_triples:
             self.train_to_filter.own((s, p)).append(o)

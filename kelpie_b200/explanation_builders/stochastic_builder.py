@@ -57,13 +57,16 @@ class StochasticBuilder:
         self.engine = engine
         self.summarization = summarization  # object with summarize()/map_rule(), or None
         self.batch_size = batch_size        # candidates emitted per engine call in the compound phase
+        self._batched = None
 
     # -- engine access ----------------------------------------------------------------------
     def _relevances(self, pred, rules):
         """[rule] -> ([relevance], [generator snapshot after each rule])."""
-        batched = getattr(self.engine, "compute_relevances", None)
-        if batched is not None and "snapshots" in inspect.signature(batched).parameters:
-            return batched(pred, rules, snapshots=True)  # errors raised inside the engine propagate
+        if self._batched is None:  # looked up once per builder: does the engine take whole batches and return snapshots?
+            batched = getattr(self.engine, "compute_relevances", None)
+            self._batched = batched is not None and "snapshots" in inspect.signature(batched).parameters
+        if self._batched:
+            return self.engine.compute_relevances(pred, rules, snapshots=True)  # errors raised inside the engine propagate
         rels, snaps = [], []
         for r in rules:  # engines without a batch entry point (e.g. the reference's own)
             rels.append(self.engine.compute_relevance(pred, r))

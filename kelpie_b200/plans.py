@@ -17,10 +17,13 @@ import torch
 def _rows_with_inverses(facts, num_relations):
     """triples + inverse triples (dataset.py:319-331; *_optimizer.py train())."""
     f = np.asarray(facts, dtype=np.int64).reshape(-1, 3)
-    inv = f.copy()
-    inv[:, 0], inv[:, 2] = f[:, 2], f[:, 0]
-    inv[:, 1] = f[:, 1] + num_relations
-    return np.vstack((f, inv)) if len(f) else np.zeros((0, 3), dtype=np.int64)
+    t = len(f)
+    out = np.empty((2 * t, 3), dtype=np.int64)
+    out[:t] = f
+    out[t:, 0] = f[:, 2]
+    out[t:, 1] = f[:, 1] + num_relations
+    out[t:, 2] = f[:, 0]
+    return out
 
 
 class HostReplay:
@@ -38,6 +41,7 @@ class HostReplay:
     callers keep the per-call path."""
 
     _N, _SIZE = 624, 5056
+    split_calls = os.environ.get("KELPIE_HOST_REPLAY") == "split"  # A/B: two native calls per TransE job instead of the fused one
     MAX_HIGH = 1 << 28  # torch 2.11 reduces 64-bit words (two generator words per element) from this range on
     _ok = None
     _lib = None
@@ -234,7 +238,7 @@ def draw_transe_compact(facts, num_relations, n_ent_with_mimic, hp, fast_rng=Non
         coin = fast_rng.integers(0, 2, (E, n))
     elif n_ent_with_mimic < HostReplay.MAX_HIGH and HostReplay.available():
         # numpy's generator is independent of torch's: interleaving the shuffles with the corruptions draws the same numbers
-        if os.environ.get("KELPIE_HOST_REPLAY") != "split":
+        if not HostReplay.split_calls:
             pos_idx, code = HostReplay.transe_job(E, n, ratio, n_ent_with_mimic)
             return n, rows.astype(np.int32), pos_idx, code
         perm = HostReplay.numpy_shuffles(E, n)  # A/B: the two separate native calls

@@ -326,11 +326,11 @@ def test_native_replay_and_per_call_draws_agree():
 
     a, b = run(True), run(False)  # native: one fused call per TransE job (kp_replay_transe_job)
     assert len(a) == len(b) and all(np.array_equal(x, y) for x, y in zip(a, b))
-    os.environ["KELPIE_HOST_REPLAY"] = "split"  # the two separate native calls (shuffles, corruptions)
+    plans.HostReplay.split_calls = True  # the two separate native calls (shuffles, corruptions); KELPIE_HOST_REPLAY=split
     try:
         c = run(True)
     finally:
-        del os.environ["KELPIE_HOST_REPLAY"]
+        plans.HostReplay.split_calls = False
     assert len(a) == len(c) and all(np.array_equal(x, y) and x.dtype == y.dtype for x, y in zip(a, c))
 
 
