@@ -395,3 +395,24 @@ def test_filter_facts_equal_the_to_filter_dict_after_edits():
     assert same()
     ds.remove_training_triple((1, 2, 3))
     assert same()
+
+
+def test_fused_replay_call_rejects_foreign_generator_layouts():
+    """kp_replay_transe_job takes torch's generator as the get_rng_state() buffer: anything but the 5056-byte layout it
+    knows (or a corrupt position) is refused instead of being walked."""
+    import ctypes
+    from kelpie_b200 import runtime
+    lib = runtime.load_library()
+    key = np.zeros(624, dtype=np.uint32)
+    pos = np.array([624], dtype=np.int32)
+    out = np.zeros(10, dtype=np.int32)
+    good = np.zeros(5056, dtype=np.uint8)
+    good[8:12].view(np.int32)[0] = 1  # freshly seeded: left = 1, next = 0
+    args = (2, 5, 1, 100, out.ctypes.data, out.ctypes.data)
+    assert lib.kp_replay_transe_job(key.ctypes.data, pos.ctypes.data, good.ctypes.data, 5056, *args) == 0
+    assert lib.kp_replay_transe_job(key.ctypes.data, pos.ctypes.data, good.ctypes.data, 5048, *args) != 0
+    bad = good.copy()
+    bad[16:24].view(np.uint64)[0] = 9999  # next beyond the 624 words
+    bad[8:12].view(np.int32)[0] = 5
+    assert lib.kp_replay_transe_job(key.ctypes.data, pos.ctypes.data, bad.ctypes.data, 5056, *args) != 0
+    assert lib.kp_replay_transe_job(key.ctypes.data, pos.ctypes.data, good.ctypes.data, 5056, 2, 5, 0, 100, out.ctypes.data, out.ctypes.data) != 0
